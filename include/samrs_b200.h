@@ -1,0 +1,83 @@
+/* samrs_b200 -- C ABI of the Blackwell-native SAM box-prompted mask engine.
+ *
+ * The reference has no FFI on this path: its boundary is the Python class surface of the vendored
+ * segment_anything package.  These entry points are what a maintainer binds underneath
+ * that surface (ctypes stub in INTEGRATION.md); each cites the reference call it replaces, paths
+ * relative to "/root/reference/Generate Dataset/segment_anything/".
+ *
+ * Conventions: every function returns 0 on success and non-zero on failure (never throws);
+ * samrs_last_error() gives the message.  One engine per (GPU, stream); not thread-safe per handle.
+ * The caller owns all buffers; pointers are DEVICE pointers unless stated; all work is enqueued
+ * asynchronously on `stream` (a cudaStream_t passed as void*), nothing synchronises the device.
+ */
+#ifndef SAMRS_B200_H
+#define SAMRS_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* replaces _build_sam(encoder_embed_dim, encoder_depth, encoder_num_heads, encoder_global_attn_indexes)
+ * -- build_sam.py:55-101.  Geometry outside these four numbers is fixed exactly as there. */
+int samrs_create(int device, int embed_dim, int depth, int num_heads, const int* global_attn_indexes,
+                 int n_global, void** engine_out);
+
+/* replaces sam.load_state_dict(state_dict) -- build_sam.py:102-106 (strict: every key of
+ * Sam.state_dict() must be present with the right element count).  names[i] are state-dict keys,
+ * dev_ptrs[i] fp32 device tensors in the reference layout; the engine repacks into its own storage,
+ * so the caller may free them after the stream has drained. */
+int samrs_load_weights(void* engine, int n, const char* const* names, const void* const* dev_ptrs,
+                       const int64_t* numel, void* stream);
+
+/* replaces Sam.preprocess + ImageEncoderViT.forward as called by SamPredictor.set_torch_image
+ * -- predictor.py:88-89, modeling/sam.py:164-174, modeling/image_encoder.py:106-116.
+ * img: uint8, HWC (chw=0) or CHW (chw=1), H,W <= 1024 (already resized so the long side is 1024).
+ * features_out: (1,256,64,64) fp32 NCHW, may be NULL.  The embedding is also cached in the engine. */
+int samrs_encode(void* engine, const uint8_t* img, int H, int W, int chw, float* features_out, void* stream);
+
+/* installs a caller-supplied image embedding (the documented "assign predictor.features by hand" use);
+ * features: (1,256,64,64) fp32 NCHW. */
+int samrs_set_features(void* engine, const float* features, void* stream);
+
+/* replaces PromptEncoder.forward + MaskDecoder.forward as called by SamPredictor.predict_torch
+ * -- predictor.py:222-235, modeling/prompt_encoder.py:128-173, modeling/mask_decoder.py:71-174.
+ * boxes (B,4) xyxy | points (B,NP,2) + labels (B,NP) int32 | mask_in (B,1,256,256), each may be NULL,
+ * all in the 1024 input frame.  lowres_out (B,C,256,256), iou_out (B,C); C = 3 if multimask else 1. */
+int samrs_decode(void* engine, const float* boxes, const float* points, const int* labels, int NP,
+                 const float* mask_in, int B, int multimask, float* lowres_out, float* iou_out, void* stream);
+
+/* replaces Sam.postprocess_masks + threshold -- modeling/sam.py:133-162, predictor.py:240-243.
+ * lowres (NB,256,256) -> bilinear to 1024, crop to (in_h,in_w), bilinear to (out_h,out_w).
+ * masks_out (NB,out_h,out_w) uint8 0/1 (== torch.bool storage) and/or logits_out fp32; either may be NULL. */
+int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int in_w, int out_h, int out_w,
+                      uint8_t* masks_out, float* logits_out, void* stream);
+
+/* fuses postprocess + threshold + the driver's painter reduce
+ * -- Generate Dataset/main_sam_hbox_semantic.py:162,195-199: label_map (H,W) uint8 is updated in place;
+ * every pixel takes class_ids[j] of the highest j whose mask is true, else keeps its value (initialise to 255).
+ * Currently H = W = 1024. */
+int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_ids, int B,
+                          uint8_t* label_map_inout, int H, int W, void* stream);
+
+/* kernels launched by this engine since creation (bench.py's gpu_launches). */
+int samrs_launch_count(void* engine, int64_t* count_out);
+
+const char* samrs_last_error(void* engine);   /* engine may be NULL: last error of a failed samrs_create */
+void samrs_destroy(void* engine);
+
+/* ---- kernel-level test hooks (used by tests/ only; same kernels the engine launches) ---- */
+/* C[M,N] = act(A[M,K] B[N,K]^T + bias + res) through the tcgen05 GEMM; A,B fp16; out fp16 or fp32. */
+int samrs_test_gemm(void* engine, const void* A, const void* B, int M, int N, int K, void* out, int out_half,
+                    const float* bias, const float* res, int act_gelu, int force_bn, void* stream);
+/* encoder attention of one block on a (4096, 3*D) fp16 qkv activation; out (4096, D) fp16. */
+int samrs_test_attention(void* engine, const void* qkv, const float* rel_pos_h, const float* rel_pos_w,
+                         int global_block, void* out, void* stream);
+/* fp32 CUDA-core GEMM of the decoder: C = act(A W^T + bias), act 0 none / 1 relu / 2 gelu. */
+int samrs_test_sgemm(void* engine, const float* A, const float* W, float* C, const float* bias, int M, int N,
+                     int K, int act, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,951 @@
+// samrs_b200 engine: weight ingest, encoder / decoder orchestration and the C ABI (include/samrs_b200.h).
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/samrs_b200.h"
+#include "attn_tc.cuh"
+#include "common.cuh"
+#include "gemm_tc.cuh"
+#include "simt.cuh"
+
+namespace samrs {
+
+static thread_local std::string g_last_error;
+
+int fail(const char* file, int line, const char* msg) {
+  char buf[512];
+  snprintf(buf, sizeof(buf), "%s:%d: %s", file, line, msg);
+  g_last_error = buf;
+  return 1;
+}
+#define SAMRS_FAIL(msg) return samrs::fail(__FILE__, __LINE__, msg)
+#define SAMRS_TRY(expr)          \
+  do {                           \
+    int _rc = (expr);            \
+    if (_rc != 0) return _rc;    \
+  } while (0)
+
+// ------------------------------------------------------------------ tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t outer, uint64_t pitch_bytes,
+                 uint32_t box_inner, uint32_t box_outer) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) SAMRS_FAIL("cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {pitch_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) SAMRS_FAIL("cuTensorMapEncodeTiled(2d) failed");
+  return 0;
+}
+int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
+                 uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) SAMRS_FAIL("cuTensorMapEncodeTiled unavailable");
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {pitch1_bytes, pitch2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t es[3] = {1, 1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<void*>(base), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) SAMRS_FAIL("cuTensorMapEncodeTiled(3d) failed");
+  return 0;
+}
+
+// ------------------------------------------------------------------ GEMM launcher
+static int64_t* g_launch_counter = nullptr;   // points into the active engine
+static inline void count_launch(int n = 1) {
+  if (g_launch_counter) *g_launch_counter += n;
+}
+
+template <int BN, bool OH, int ACT>
+static int launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, int grid, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAMRS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OH, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  gemm_tc_kernel<BN, OH, ACT><<<grid, 256, Cfg::kSmemBytes, st>>>(tA, tB, p);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const GemmParams& pin, bool out_half, int act,
+                   int num_sms, cudaStream_t stream, int force_bn) {
+  GemmParams p = pin;
+  if (p.K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) SAMRS_FAIL("gemm: K and leading dimensions must be multiples of 8");
+  int bn = force_bn;
+  if (bn == 0) {
+    // choose the N tile with the best useful-work / (waves * tile cost) ratio
+    const int cands[3] = {256, 160, 128};
+    double best = -1.0;
+    for (int i = 0; i < 3; ++i) {
+      const int c = cands[i];
+      const long tm = (p.M + GEMM_BM - 1) / GEMM_BM, tn = (p.N + c - 1) / c;
+      const long waves = (tm * tn + num_sms - 1) / num_sms;
+      const double eff = double(p.M) * p.N / (double(waves) * num_sms * GEMM_BM * c);
+      if (eff > best + 1e-9) { best = eff; bn = c; }
+    }
+  }
+  p.tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  p.tiles_n = (p.N + bn - 1) / bn;
+  CUtensorMap tA, tB;
+  SAMRS_TRY(make_tmap_2d(&tA, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, GEMM_BK, GEMM_BM));
+  SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t(bn)));
+  const int tiles = p.tiles_m * p.tiles_n;
+  const int grid = tiles < num_sms ? tiles : num_sms;
+#define SAMRS_GEMM_CASE(BN_)                                                                        \
+  if (bn == BN_) {                                                                                  \
+    if (out_half && act == 0) return launch_gemm_inst<BN_, true, 0>(tA, tB, p, grid, stream);       \
+    if (out_half && act == 1) return launch_gemm_inst<BN_, true, 1>(tA, tB, p, grid, stream);       \
+    if (!out_half && act == 0) return launch_gemm_inst<BN_, false, 0>(tA, tB, p, grid, stream);     \
+    SAMRS_FAIL("gemm: unsupported epilogue");                                                       \
+  }
+  SAMRS_GEMM_CASE(256)
+  SAMRS_GEMM_CASE(160)
+  SAMRS_GEMM_CASE(128)
+#undef SAMRS_GEMM_CASE
+  SAMRS_FAIL("gemm: unsupported N tile");
+}
+
+// ------------------------------------------------------------------ engine state
+struct BlockWeights {
+  float *ln1w, *ln1b, *ln2w, *ln2b;
+  __half *wqkv, *wproj, *w1, *w2;
+  float *bqkv_eff, *bproj_eff, *b1, *b2;
+  float *rph, *rpw;
+  bool global;
+};
+
+struct DecAttn {  // decoder Attention weights (fp32)
+  float *wq, *bq, *wk, *bk, *wv, *bv, *wo, *bo;
+  int internal;
+};
+struct DecLayer {
+  DecAttn self_attn, t2i, i2t;
+  float *n1w, *n1b, *n2w, *n2b, *n3w, *n3b, *n4w, *n4b;
+  float *m1w, *m1b, *m2w, *m2b;
+};
+struct Mlp3 { float *w[3], *b[3]; };
+
+struct Engine {
+  int device = 0;
+  int D = 0, depth = 0, heads = 0, hd = 0;
+  std::vector<int> global_idx;
+  int num_sms = 148;
+  int64_t launches = 0;
+  std::string err;
+  std::vector<void*> allocs;
+  bool weights_loaded = false, image_set = false;
+
+  // encoder weights
+  __half* w_patch = nullptr; float* b_patch = nullptr; float* pos_embed = nullptr;
+  std::vector<BlockWeights> blocks;
+  __half* w_neck0 = nullptr; __half* w_neck2 = nullptr;
+  float *neck1w = nullptr, *neck1b = nullptr, *neck3w = nullptr, *neck3b = nullptr;
+  // prompt encoder
+  float *gauss = nullptr, *point_emb = nullptr, *not_a_point = nullptr, *no_mask = nullptr;
+  float *md_w0, *md_b0, *md_g1, *md_be1, *md_w3, *md_b3, *md_g4, *md_be4, *md_w6, *md_b6;
+  // decoder
+  DecLayer dl[2];
+  DecAttn final_attn;
+  float *nfw, *nfb, *iou_token, *mask_tokens;
+  float *up_w1r, *up_b1r, *up_lnw, *up_lnb, *up_w2r, *up_b2;
+  Mlp3 hyper[4], iou_head;
+  float* dense_pe = nullptr;           // [4096][256]
+  float* pek[5] = {nullptr};           // dense_pe * W^T for: l0.t2i.k, l0.i2t.q, l1.t2i.k, l1.i2t.q, final.k  [4096][128]
+
+  // encoder activations
+  __half *a_pe, *xn, *qkv, *attn_o, *hid, *x16, *neck_ln16, *neck_col;
+  float *x, *rel, *neck0, *neck2, *feat_tok, *feat_nchw;
+  // per-image decoder cache
+  float *src0, *K0, *V0, *Qi0;
+  float* pp_full = nullptr;            // postprocess scratch for non-1024 sizes
+  // decoder scratch (sized for dec_cap prompts)
+  int dec_cap = 0;
+  float *d_tok0, *d_q, *d_tmp256a, *d_tmp256b, *d_tmp256c, *d_tmp256d, *d_tmp128a, *d_tmp128b, *d_tmp128c, *d_mlp;
+  float *d_keys, *d_io, *d_Kp, *d_Vp, *d_Qp, *d_u1, *d_src, *d_hyper, *d_hy_t, *d_hy_a, *d_hy_b, *d_iou_all, *d_low;
+
+  template <typename T>
+  int alloc(T** p, size_t n) {
+    void* q = nullptr;
+    if (cudaMalloc(&q, n * sizeof(T) + 256) != cudaSuccess) return samrs::fail(__FILE__, __LINE__, "cudaMalloc failed");
+    allocs.push_back(q);
+    *p = reinterpret_cast<T*>(q);
+    return 0;
+  }
+};
+
+static int set_err(Engine* e, int rc) {
+  if (rc != 0 && e) e->err = g_last_error;
+  return rc;
+}
+
+// ------------------------------------------------------------------ small launch helpers
+static int sgemm(cudaStream_t st, const float* A, int lda, const float* W, int ldw, float* C, int ldc, const float* bias,
+                 const float* R, int ldr, int rmod, int M, int N, int K, int act) {
+  if (K % 16 != 0 || lda % 4 != 0 || ldw % 4 != 0) SAMRS_FAIL("sgemm: K must be a multiple of 16");
+  SgemmParams p{A, lda, W, ldw, C, ldc, bias, R, ldr, rmod, M, N, K, act};
+  dim3 grid((M + 127) / 128, (N + 63) / 64);
+  sgemm_tn_kernel<<<grid, 256, 0, st>>>(p);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+template <typename OutT, int ACT>
+static int ln_rows(cudaStream_t st, const float* in, int ld_in, const float* g, const float* b, float eps, OutT* out, int ld_out,
+                   int rows, int C) {
+  const int nv = C / 4;
+  const int threads = 256, rows_per_block = threads / 32;
+  const int grid = (rows + rows_per_block - 1) / rows_per_block;
+  if (C % 4 != 0) SAMRS_FAIL("layernorm: C must be a multiple of 4");
+  if (nv <= 32) ln_rows_kernel<OutT, ACT, 1><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
+  else if (nv <= 64) ln_rows_kernel<OutT, ACT, 2><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
+  else if (nv <= 192) ln_rows_kernel<OutT, ACT, 6><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
+  else if (nv <= 320) ln_rows_kernel<OutT, ACT, 10><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
+  else SAMRS_FAIL("layernorm: C too large");
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+template <int HD>
+static int launch_relpos(cudaStream_t st, const __half* qkv, int ld, const float* rph, const float* rpw, int S, int heads, float* rel) {
+  const int L = 2 * S - 1;
+  const size_t smem = (size_t(2) * L * (HD + 1) + 8 * HD) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAMRS_CUDA_OK(cudaFuncSetAttribute(relpos_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr_done = true;
+  }
+  dim3 grid(4096 / 8, heads);
+  relpos_kernel<HD><<<grid, 256, smem, st>>>(qkv, ld, rph, rpw, S, rel);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+template <int HD, int BX, int QBY, int KBY, int NKT>
+static int launch_attn_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, const AttnParams& p, int num_sms, cudaStream_t st) {
+  using C = AttnCfg<HD, BX, QBY, KBY, NKT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAMRS_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<HD, BX, QBY, KBY, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_done = true;
+  }
+  const int items = p.num_qtiles * p.heads;
+  const int grid = items < num_sms ? items : num_sms;
+  attn_tc_kernel<HD, BX, QBY, KBY, NKT><<<grid, 256, C::kSmemBytes, st>>>(tQ, tKV, p);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// encoder attention of one block: rel-pos terms + tcgen05 attention.  qkv: [4096][3D] fp16.
+static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, const float* rph, const float* rpw, bool global,
+                             __half* out) {
+  const int D = e->D, hd = e->hd, S = global ? 64 : 14;
+  if (hd == 64) SAMRS_TRY(launch_relpos<64>(st, qkv, 3 * D, rph, rpw, S, e->heads, e->rel));
+  else if (hd == 80) SAMRS_TRY(launch_relpos<80>(st, qkv, 3 * D, rph, rpw, S, e->heads, e->rel));
+  else SAMRS_FAIL("head_dim must be 64 or 80");
+  AttnParams p;
+  p.rel = e->rel;
+  p.out = out;
+  p.D = D;
+  p.heads = e->heads;
+  p.scale_log2e = (1.0f / sqrtf(float(hd))) * 1.4426950408889634f;
+  CUtensorMap tQ, tKV;
+  const uint64_t pitch_x = uint64_t(3 * D) * 2, pitch_y = pitch_x * 64;
+  if (global) {
+    p.num_qtiles = 32;
+    SAMRS_TRY(make_tmap_3d(&tQ, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 64, 2));
+    tKV = tQ;
+    if (hd == 64) return launch_attn_inst<64, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
+    return launch_attn_inst<80, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
+  }
+  p.num_qtiles = 50;
+  SAMRS_TRY(make_tmap_3d(&tQ, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 14, 7));
+  SAMRS_TRY(make_tmap_3d(&tKV, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 14, 14));
+  if (hd == 64) return launch_attn_inst<64, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
+  return launch_attn_inst<80, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
+}
+
+// ------------------------------------------------------------------ weight ingest
+struct Src { const float* p; int64_t n; };
+typedef std::unordered_map<std::string, Src> SrcMap;
+
+static int need(const SrcMap& m, const std::string& k, int64_t n, const float** out) {
+  auto it = m.find(k);
+  if (it == m.end()) return samrs::fail(__FILE__, __LINE__, ("missing key in state_dict: " + k).c_str());
+  if (it->second.n != n) return samrs::fail(__FILE__, __LINE__, ("size mismatch for " + k).c_str());
+  *out = it->second.p;
+  return 0;
+}
+
+__global__ void zero_range_kernel(float* p, int from, int to) {
+  const int i = from + blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < to) p[i] = 0.f;
+}
+// neck.2.weight [256][256][3][3] -> [256][tap*256 + ci] fp16
+__global__ void repack_neck3x3_kernel(const float* __restrict__ w, __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 256 * 2304) return;
+  const int co = i / 2304, r = i % 2304, tap = r / 256, ci = r % 256;
+  out[i] = __float2half_rn(w[(size_t(co) * 256 + ci) * 9 + tap]);
+}
+// ConvTranspose2d weight [Cin][Cout][2][2] -> [(dy*2+dx)*Cout + co][ci]
+__global__ void repack_convT_kernel(const float* __restrict__ w, float* __restrict__ out, int Cin, int Cout) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 4 * Cout * Cin) return;
+  const int ci = i % Cin, co = (i / Cin) % Cout, d = i / (Cin * Cout);
+  out[i] = w[(size_t(ci) * Cout + co) * 4 + d];
+}
+__global__ void tile_bias_kernel(const float* __restrict__ b, float* __restrict__ out, int C, int reps) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < C * reps) out[i] = b[i % C];
+}
+
+static int copy_f32(Engine* e, cudaStream_t st, const float* src, int64_t n, float** dst) {
+  SAMRS_TRY(e->alloc(dst, size_t(n)));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(*dst, src, size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+static int to_half(Engine* e, cudaStream_t st, const float* src, int64_t n, __half** dst) {
+  if (n % 4 != 0) SAMRS_FAIL("to_half: size must be a multiple of 4");
+  SAMRS_TRY(e->alloc(dst, size_t(n)));
+  const size_t n4 = size_t(n) / 4;
+  cast_f32_f16_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(src, *dst, n4);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int load_dec_attn(Engine* e, cudaStream_t st, const SrcMap& m, const std::string& pre, int internal, DecAttn* a) {
+  const float* s;
+  a->internal = internal;
+  SAMRS_TRY(need(m, pre + ".q_proj.weight", int64_t(internal) * 256, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(internal) * 256, &a->wq));
+  SAMRS_TRY(need(m, pre + ".q_proj.bias", internal, &s));                  SAMRS_TRY(copy_f32(e, st, s, internal, &a->bq));
+  SAMRS_TRY(need(m, pre + ".k_proj.weight", int64_t(internal) * 256, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(internal) * 256, &a->wk));
+  SAMRS_TRY(need(m, pre + ".k_proj.bias", internal, &s));                  SAMRS_TRY(copy_f32(e, st, s, internal, &a->bk));
+  SAMRS_TRY(need(m, pre + ".v_proj.weight", int64_t(internal) * 256, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(internal) * 256, &a->wv));
+  SAMRS_TRY(need(m, pre + ".v_proj.bias", internal, &s));                  SAMRS_TRY(copy_f32(e, st, s, internal, &a->bv));
+  SAMRS_TRY(need(m, pre + ".out_proj.weight", int64_t(internal) * 256, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(internal) * 256, &a->wo));
+  SAMRS_TRY(need(m, pre + ".out_proj.bias", 256, &s));                     SAMRS_TRY(copy_f32(e, st, s, 256, &a->bo));
+  return 0;
+}
+static int load_pair(Engine* e, cudaStream_t st, const SrcMap& m, const std::string& pre, int64_t n, float** w, float** b) {
+  const float* s;
+  SAMRS_TRY(need(m, pre + ".weight", n, &s)); SAMRS_TRY(copy_f32(e, st, s, n, w));
+  SAMRS_TRY(need(m, pre + ".bias", n, &s));   SAMRS_TRY(copy_f32(e, st, s, n, b));
+  return 0;
+}
+static int load_mlp3(Engine* e, cudaStream_t st, const SrcMap& m, const std::string& pre, int out_dim, Mlp3* mlp) {
+  const int dims[4] = {256, 256, 256, out_dim};
+  for (int j = 0; j < 3; ++j) {
+    const float* s;
+    const std::string k = pre + ".layers." + std::to_string(j);
+    SAMRS_TRY(need(m, k + ".weight", int64_t(dims[j + 1]) * dims[j], &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(dims[j + 1]) * dims[j], &mlp->w[j]));
+    SAMRS_TRY(need(m, k + ".bias", dims[j + 1], &s));                      SAMRS_TRY(copy_f32(e, st, s, dims[j + 1], &mlp->b[j]));
+  }
+  return 0;
+}
+
+static int load_weights_impl(Engine* e, const SrcMap& m, cudaStream_t st) {
+  const int D = e->D;
+  const int64_t D64 = D;
+  const float* s;
+  const std::string ie = "image_encoder.";
+  SAMRS_TRY(need(m, ie + "pos_embed", 4096 * D64, &s));               SAMRS_TRY(copy_f32(e, st, s, 4096 * D64, &e->pos_embed));
+  SAMRS_TRY(need(m, ie + "patch_embed.proj.weight", D64 * 768, &s));  SAMRS_TRY(to_half(e, st, s, D64 * 768, &e->w_patch));
+  SAMRS_TRY(need(m, ie + "patch_embed.proj.bias", D64, &s));          SAMRS_TRY(copy_f32(e, st, s, D64, &e->b_patch));
+  e->blocks.resize(e->depth);
+  for (int i = 0; i < e->depth; ++i) {
+    BlockWeights& b = e->blocks[i];
+    const std::string p = ie + "blocks." + std::to_string(i) + ".";
+    b.global = false;
+    for (int gidx : e->global_idx) b.global |= (gidx == i);
+    const int S = b.global ? 64 : 14;
+    SAMRS_TRY(load_pair(e, st, m, p + "norm1", D64, &b.ln1w, &b.ln1b));
+    SAMRS_TRY(load_pair(e, st, m, p + "norm2", D64, &b.ln2w, &b.ln2b));
+    SAMRS_TRY(need(m, p + "attn.rel_pos_h", int64_t(2 * S - 1) * e->hd, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(2 * S - 1) * e->hd, &b.rph));
+    SAMRS_TRY(need(m, p + "attn.rel_pos_w", int64_t(2 * S - 1) * e->hd, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(2 * S - 1) * e->hd, &b.rpw));
+    SAMRS_TRY(need(m, p + "attn.qkv.weight", 3 * D64 * D64, &s));             SAMRS_TRY(to_half(e, st, s, 3 * D64 * D64, &b.wqkv));
+    const float* bqkv;
+    SAMRS_TRY(need(m, p + "attn.qkv.bias", 3 * D64, &bqkv));
+    // K bias cancels in the softmax, V bias moves into the proj bias (see attn_tc.cuh header)
+    SAMRS_TRY(copy_f32(e, st, bqkv, 3 * D64, &b.bqkv_eff));
+    zero_range_kernel<<<(2 * D + 255) / 256, 256, 0, st>>>(b.bqkv_eff, D, 3 * D);
+    const float *wproj, *bproj;
+    SAMRS_TRY(need(m, p + "attn.proj.weight", D64 * D64, &wproj));            SAMRS_TRY(to_half(e, st, wproj, D64 * D64, &b.wproj));
+    SAMRS_TRY(need(m, p + "attn.proj.bias", D64, &bproj));
+    SAMRS_TRY(e->alloc(&b.bproj_eff, size_t(D)));
+    // bproj_eff = bproj + Wproj * bv     (fp32, one-row GEMM)
+    SAMRS_TRY(sgemm(st, bqkv + 2 * D, D, wproj, D, b.bproj_eff, D, bproj, nullptr, 0, 0, 1, D, D, 0));
+    SAMRS_TRY(need(m, p + "mlp.lin1.weight", 4 * D64 * D64, &s));             SAMRS_TRY(to_half(e, st, s, 4 * D64 * D64, &b.w1));
+    SAMRS_TRY(need(m, p + "mlp.lin1.bias", 4 * D64, &s));                     SAMRS_TRY(copy_f32(e, st, s, 4 * D64, &b.b1));
+    SAMRS_TRY(need(m, p + "mlp.lin2.weight", 4 * D64 * D64, &s));             SAMRS_TRY(to_half(e, st, s, 4 * D64 * D64, &b.w2));
+    SAMRS_TRY(need(m, p + "mlp.lin2.bias", D64, &s));                         SAMRS_TRY(copy_f32(e, st, s, D64, &b.b2));
+  }
+  SAMRS_TRY(need(m, ie + "neck.0.weight", 256 * D64, &s));       SAMRS_TRY(to_half(e, st, s, 256 * D64, &e->w_neck0));
+  SAMRS_TRY(load_pair(e, st, m, ie + "neck.1", 256, &e->neck1w, &e->neck1b));
+  SAMRS_TRY(need(m, ie + "neck.2.weight", 256 * 2304, &s));
+  SAMRS_TRY(e->alloc(&e->w_neck2, size_t(256) * 2304));
+  repack_neck3x3_kernel<<<(256 * 2304 + 255) / 256, 256, 0, st>>>(s, e->w_neck2);
+  SAMRS_TRY(load_pair(e, st, m, ie + "neck.3", 256, &e->neck3w, &e->neck3b));
+
+  const std::string pe = "prompt_encoder.";
+  SAMRS_TRY(need(m, pe + "pe_layer.positional_encoding_gaussian_matrix", 256, &s)); SAMRS_TRY(copy_f32(e, st, s, 256, &e->gauss));
+  SAMRS_TRY(e->alloc(&e->point_emb, 4 * 256));
+  for (int i = 0; i < 4; ++i) {
+    SAMRS_TRY(need(m, pe + "point_embeddings." + std::to_string(i) + ".weight", 256, &s));
+    SAMRS_CUDA_OK(cudaMemcpyAsync(e->point_emb + i * 256, s, 1024, cudaMemcpyDeviceToDevice, st));
+  }
+  SAMRS_TRY(need(m, pe + "not_a_point_embed.weight", 256, &s)); SAMRS_TRY(copy_f32(e, st, s, 256, &e->not_a_point));
+  SAMRS_TRY(need(m, pe + "no_mask_embed.weight", 256, &s));     SAMRS_TRY(copy_f32(e, st, s, 256, &e->no_mask));
+  SAMRS_TRY(need(m, pe + "mask_downscaling.0.weight", 16, &s)); SAMRS_TRY(copy_f32(e, st, s, 16, &e->md_w0));
+  SAMRS_TRY(need(m, pe + "mask_downscaling.0.bias", 4, &s));    SAMRS_TRY(copy_f32(e, st, s, 4, &e->md_b0));
+  SAMRS_TRY(load_pair(e, st, m, pe + "mask_downscaling.1", 4, &e->md_g1, &e->md_be1));
+  SAMRS_TRY(need(m, pe + "mask_downscaling.3.weight", 256, &s)); SAMRS_TRY(copy_f32(e, st, s, 256, &e->md_w3));
+  SAMRS_TRY(need(m, pe + "mask_downscaling.3.bias", 16, &s));    SAMRS_TRY(copy_f32(e, st, s, 16, &e->md_b3));
+  SAMRS_TRY(load_pair(e, st, m, pe + "mask_downscaling.4", 16, &e->md_g4, &e->md_be4));
+  SAMRS_TRY(need(m, pe + "mask_downscaling.6.weight", 4096, &s)); SAMRS_TRY(copy_f32(e, st, s, 4096, &e->md_w6));
+  SAMRS_TRY(need(m, pe + "mask_downscaling.6.bias", 256, &s));    SAMRS_TRY(copy_f32(e, st, s, 256, &e->md_b6));
+
+  const std::string md = "mask_decoder.";
+  for (int i = 0; i < 2; ++i) {
+    DecLayer& L = e->dl[i];
+    const std::string p = md + "transformer.layers." + std::to_string(i);
+    SAMRS_TRY(load_dec_attn(e, st, m, p + ".self_attn", 256, &L.self_attn));
+    SAMRS_TRY(load_dec_attn(e, st, m, p + ".cross_attn_token_to_image", 128, &L.t2i));
+    SAMRS_TRY(load_dec_attn(e, st, m, p + ".cross_attn_image_to_token", 128, &L.i2t));
+    SAMRS_TRY(load_pair(e, st, m, p + ".norm1", 256, &L.n1w, &L.n1b));
+    SAMRS_TRY(load_pair(e, st, m, p + ".norm2", 256, &L.n2w, &L.n2b));
+    SAMRS_TRY(load_pair(e, st, m, p + ".norm3", 256, &L.n3w, &L.n3b));
+    SAMRS_TRY(load_pair(e, st, m, p + ".norm4", 256, &L.n4w, &L.n4b));
+    SAMRS_TRY(need(m, p + ".mlp.lin1.weight", 2048 * 256, &s)); SAMRS_TRY(copy_f32(e, st, s, 2048 * 256, &L.m1w));
+    SAMRS_TRY(need(m, p + ".mlp.lin1.bias", 2048, &s));         SAMRS_TRY(copy_f32(e, st, s, 2048, &L.m1b));
+    SAMRS_TRY(need(m, p + ".mlp.lin2.weight", 2048 * 256, &s)); SAMRS_TRY(copy_f32(e, st, s, 2048 * 256, &L.m2w));
+    SAMRS_TRY(need(m, p + ".mlp.lin2.bias", 256, &s));          SAMRS_TRY(copy_f32(e, st, s, 256, &L.m2b));
+  }
+  SAMRS_TRY(load_dec_attn(e, st, m, md + "transformer.final_attn_token_to_image", 128, &e->final_attn));
+  SAMRS_TRY(load_pair(e, st, m, md + "transformer.norm_final_attn", 256, &e->nfw, &e->nfb));
+  SAMRS_TRY(need(m, md + "iou_token.weight", 256, &s));    SAMRS_TRY(copy_f32(e, st, s, 256, &e->iou_token));
+  SAMRS_TRY(need(m, md + "mask_tokens.weight", 1024, &s)); SAMRS_TRY(copy_f32(e, st, s, 1024, &e->mask_tokens));
+  const float *w1, *b1, *w2;
+  SAMRS_TRY(need(m, md + "output_upscaling.0.weight", 256 * 64 * 4, &w1));
+  SAMRS_TRY(need(m, md + "output_upscaling.0.bias", 64, &b1));
+  SAMRS_TRY(e->alloc(&e->up_w1r, 256 * 256));
+  SAMRS_TRY(e->alloc(&e->up_b1r, 256));
+  repack_convT_kernel<<<(4 * 64 * 256 + 255) / 256, 256, 0, st>>>(w1, e->up_w1r, 256, 64);
+  tile_bias_kernel<<<1, 256, 0, st>>>(b1, e->up_b1r, 64, 4);
+  SAMRS_TRY(load_pair(e, st, m, md + "output_upscaling.1", 64, &e->up_lnw, &e->up_lnb));
+  SAMRS_TRY(need(m, md + "output_upscaling.3.weight", 64 * 32 * 4, &w2));
+  SAMRS_TRY(e->alloc(&e->up_w2r, 4 * 32 * 64));
+  repack_convT_kernel<<<(4 * 32 * 64 + 255) / 256, 256, 0, st>>>(w2, e->up_w2r, 64, 32);
+  SAMRS_TRY(need(m, md + "output_upscaling.3.bias", 32, &s)); SAMRS_TRY(copy_f32(e, st, s, 32, &e->up_b2));
+  for (int i = 0; i < 4; ++i) SAMRS_TRY(load_mlp3(e, st, m, md + "output_hypernetworks_mlps." + std::to_string(i), 32, &e->hyper[i]));
+  SAMRS_TRY(load_mlp3(e, st, m, md + "iou_prediction_head", 4, &e->iou_head));
+
+  // constants of the model: dense positional encoding and its five 256->128 projections
+  SAMRS_TRY(e->alloc(&e->dense_pe, size_t(4096) * 256));
+  dense_pe_kernel<<<4096, 128, 0, st>>>(e->gauss, e->dense_pe);
+  const float* pw[5] = {e->dl[0].t2i.wk, e->dl[0].i2t.wq, e->dl[1].t2i.wk, e->dl[1].i2t.wq, e->final_attn.wk};
+  for (int i = 0; i < 5; ++i) {
+    SAMRS_TRY(e->alloc(&e->pek[i], size_t(4096) * 128));
+    SAMRS_TRY(sgemm(st, e->dense_pe, 256, pw[i], 256, e->pek[i], 128, nullptr, nullptr, 0, 0, 4096, 128, 256, 0));
+  }
+  SAMRS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int alloc_activations(Engine* e) {
+  const size_t D = e->D, T = 4096;
+  SAMRS_TRY(e->alloc(&e->a_pe, T * 768));
+  SAMRS_TRY(e->alloc(&e->x, T * D));
+  SAMRS_TRY(e->alloc(&e->xn, T * D));
+  SAMRS_TRY(e->alloc(&e->qkv, T * 3 * D));
+  SAMRS_TRY(e->alloc(&e->rel, size_t(e->heads) * T * 128));
+  SAMRS_TRY(e->alloc(&e->attn_o, T * D));
+  SAMRS_TRY(e->alloc(&e->hid, T * 4 * D));
+  SAMRS_TRY(e->alloc(&e->x16, T * D));
+  SAMRS_TRY(e->alloc(&e->neck0, T * 256));
+  SAMRS_TRY(e->alloc(&e->neck_ln16, T * 256));
+  SAMRS_TRY(e->alloc(&e->neck_col, T * 2304));
+  SAMRS_TRY(e->alloc(&e->neck2, T * 256));
+  SAMRS_TRY(e->alloc(&e->feat_tok, T * 256));
+  SAMRS_TRY(e->alloc(&e->feat_nchw, T * 256));
+  SAMRS_TRY(e->alloc(&e->src0, T * 256));
+  SAMRS_TRY(e->alloc(&e->K0, T * 128));
+  SAMRS_TRY(e->alloc(&e->V0, T * 128));
+  SAMRS_TRY(e->alloc(&e->Qi0, T * 128));
+  return 0;
+}
+
+static int ensure_decoder_scratch(Engine* e, int B) {
+  if (B <= e->dec_cap) return 0;
+  // scratch is never freed individually; grow geometrically (old buffers are released with the engine)
+  int cap = e->dec_cap ? e->dec_cap : 32;
+  while (cap < B) cap *= 2;
+  const size_t c = cap, TT = 16;
+  SAMRS_TRY(e->alloc(&e->d_tok0, c * TT * 256));
+  SAMRS_TRY(e->alloc(&e->d_q, c * TT * 256));
+  SAMRS_TRY(e->alloc(&e->d_tmp256a, c * TT * 256));
+  SAMRS_TRY(e->alloc(&e->d_tmp256b, c * TT * 256));
+  SAMRS_TRY(e->alloc(&e->d_tmp256c, c * TT * 256));
+  SAMRS_TRY(e->alloc(&e->d_tmp256d, c * TT * 256));
+  SAMRS_TRY(e->alloc(&e->d_tmp128a, c * TT * 128));
+  SAMRS_TRY(e->alloc(&e->d_tmp128b, c * TT * 128));
+  SAMRS_TRY(e->alloc(&e->d_tmp128c, c * TT * 128));
+  SAMRS_TRY(e->alloc(&e->d_mlp, c * TT * 2048));
+  SAMRS_TRY(e->alloc(&e->d_keys, c * 4096 * 256));
+  SAMRS_TRY(e->alloc(&e->d_io, c * 4096 * 128));
+  SAMRS_TRY(e->alloc(&e->d_Kp, c * 4096 * 128));
+  SAMRS_TRY(e->alloc(&e->d_Vp, c * 4096 * 128));
+  SAMRS_TRY(e->alloc(&e->d_Qp, c * 4096 * 128));
+  SAMRS_TRY(e->alloc(&e->d_u1, c * 4096 * 256));
+  SAMRS_TRY(e->alloc(&e->d_src, c * 4096 * 256));
+  SAMRS_TRY(e->alloc(&e->d_hyper, c * 4 * 32));
+  SAMRS_TRY(e->alloc(&e->d_hy_t, c * 256));
+  SAMRS_TRY(e->alloc(&e->d_hy_a, c * 256));
+  SAMRS_TRY(e->alloc(&e->d_hy_b, c * 256));
+  SAMRS_TRY(e->alloc(&e->d_iou_all, c * 4));
+  SAMRS_TRY(e->alloc(&e->d_low, c * 3 * 65536));
+  e->dec_cap = cap;
+  return 0;
+}
+
+// ------------------------------------------------------------------ encoder
+static int gemm_enc(Engine* e, cudaStream_t st, const __half* A, int lda, const __half* W, int M, int N, int K, void* out, int ldc,
+                    bool out_half, const float* bias, const float* res, int ldr, int res_mod, int act) {
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K;
+  p.out = out; p.ldc = ldc;
+  p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
+  p.tiles_m = p.tiles_n = 0;
+  return launch_gemm_tc(A, lda, W, K, p, out_half, act, e->num_sms, st, 0);
+}
+
+// per-image decoder cache: src0 = features + no_mask_embed and its three layer-0 projections
+static int build_image_cache(Engine* e, cudaStream_t st) {
+  add_rowvec_kernel<<<(4096 * 256 + 255) / 256, 256, 0, st>>>(e->feat_tok, 0, e->no_mask, e->src0, 4096, 256);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  const DecLayer& L = e->dl[0];
+  SAMRS_TRY(sgemm(st, e->src0, 256, L.t2i.wk, 256, e->K0, 128, L.t2i.bk, e->pek[0], 128, 4096, 4096, 128, 256, 0));
+  SAMRS_TRY(sgemm(st, e->src0, 256, L.t2i.wv, 256, e->V0, 128, L.t2i.bv, nullptr, 0, 0, 4096, 128, 256, 0));
+  SAMRS_TRY(sgemm(st, e->src0, 256, L.i2t.wq, 256, e->Qi0, 128, L.i2t.bq, e->pek[1], 128, 4096, 4096, 128, 256, 0));
+  e->image_set = true;
+  return 0;
+}
+
+static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, float* features_out, cudaStream_t st) {
+  if (!e->weights_loaded) SAMRS_FAIL("encode: weights not loaded");
+  if (H < 1 || W < 1 || H > 1024 || W > 1024) SAMRS_FAIL("encode: image must be at most 1024x1024 (resize the long side to 1024 first)");
+  const int D = e->D, T = 4096;
+  preprocess_im2col_kernel<<<(4096 * 48 + 255) / 256, 256, 0, st>>>(img, H, W, chw, e->a_pe);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  // patch embedding + absolute position embedding (image_encoder.py:107-109)
+  SAMRS_TRY(gemm_enc(e, st, e->a_pe, 768, e->w_patch, T, D, 768, e->x, D, false, e->b_patch, e->pos_embed, D, 0, 0));
+  for (int i = 0; i < e->depth; ++i) {
+    const BlockWeights& b = e->blocks[i];
+    SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln1w, b.ln1b, 1e-6f, e->xn, D, T, D)));
+    SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.wqkv, T, 3 * D, D, e->qkv, 3 * D, true, b.bqkv_eff, nullptr, 0, 0, 0));
+    SAMRS_TRY(encoder_attention(e, st, e->qkv, b.rph, b.rpw, b.global, e->attn_o));
+    SAMRS_TRY(gemm_enc(e, st, e->attn_o, D, b.wproj, T, D, D, e->x, D, false, b.bproj_eff, e->x, D, 0, 0));
+    SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln2w, b.ln2b, 1e-6f, e->xn, D, T, D)));
+    SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.w1, T, 4 * D, D, e->hid, 4 * D, true, b.b1, nullptr, 0, 0, 1));
+    SAMRS_TRY(gemm_enc(e, st, e->hid, 4 * D, b.w2, T, D, 4 * D, e->x, D, false, b.b2, e->x, D, 0, 0));
+  }
+  // neck (image_encoder.py:88-104)
+  cast_f32_f16_kernel<<<unsigned((size_t(T) * D / 4 + 255) / 256), 256, 0, st>>>(e->x, e->x16, size_t(T) * D / 4);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  SAMRS_TRY(gemm_enc(e, st, e->x16, D, e->w_neck0, T, 256, D, e->neck0, 256, false, nullptr, nullptr, 0, 0, 0));
+  SAMRS_TRY((ln_rows<__half, 0>(st, e->neck0, 256, e->neck1w, e->neck1b, 1e-6f, e->neck_ln16, 256, T, 256)));
+  neck_im2col3x3_kernel<<<(4096 * 9 * 32 + 255) / 256, 256, 0, st>>>(e->neck_ln16, e->neck_col);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  SAMRS_TRY(gemm_enc(e, st, e->neck_col, 2304, e->w_neck2, T, 256, 2304, e->neck2, 256, false, nullptr, nullptr, 0, 0, 0));
+  SAMRS_TRY((ln_rows<float, 0>(st, e->neck2, 256, e->neck3w, e->neck3b, 1e-6f, e->feat_tok, 256, T, 256)));
+  float* nchw = features_out ? features_out : e->feat_nchw;
+  transpose_tok_to_nchw_kernel<<<dim3(128, 8), dim3(32, 8), 0, st>>>(e->feat_tok, nchw, 256);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return build_image_cache(e, st);
+}
+
+// ------------------------------------------------------------------ decoder
+static int add2(cudaStream_t st, const float* a, const float* b, float* out, size_t n) {
+  // out = a + b (elementwise, same shape) via the row-vector kernel with C = n
+  if (out != a) SAMRS_CUDA_OK(cudaMemcpyAsync(out, a, n * 4, cudaMemcpyDeviceToDevice, st));
+  add_inplace_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(out, b, n);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+static int token_attention(Engine* e, cudaStream_t st, const DecAttn& a, const float* q_in, const float* k_in, const float* v_in,
+                           int BT, int T, int B, float* out256 /*projected*/, const float* residual) {
+  // self-attention on tokens (internal dim 256)
+  SAMRS_TRY(sgemm(st, q_in, 256, a.wq, 256, e->d_tmp256a, 256, a.bq, nullptr, 0, 0, BT, 256, 256, 0));
+  SAMRS_TRY(sgemm(st, k_in, 256, a.wk, 256, e->d_tmp256b, 256, a.bk, nullptr, 0, 0, BT, 256, 256, 0));
+  SAMRS_TRY(sgemm(st, v_in, 256, a.wv, 256, e->d_tmp256c, 256, a.bv, nullptr, 0, 0, BT, 256, 256, 0));
+  const size_t smem = (size_t(3) * T * 256 + 8 * T * T) * 4;
+  tok_self_attn_kernel<<<B, 256, smem, st>>>(e->d_tmp256a, e->d_tmp256b, e->d_tmp256c, e->d_tmp256d, T);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return sgemm(st, e->d_tmp256d, 256, a.wo, 256, out256, 256, a.bo, residual, 256, 0, BT, 256, 256, 0);
+}
+
+static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const float* points, const int* labels, int NP,
+                        const float* mask_in, int B, int multimask, float* lowres_out, float* iou_out) {
+  const int pad = (points && !boxes) ? 1 : 0;
+  const int Ns = (points ? NP + pad : 0) + (boxes ? 2 : 0);
+  const int T = 5 + Ns, BT = B * T;
+  if (T > 16) SAMRS_FAIL("decode: at most 11 sparse prompt tokens per prompt are supported");
+  SAMRS_TRY(ensure_decoder_scratch(e, B));
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAMRS_CUDA_OK(cudaFuncSetAttribute(tok_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_done = true;
+  }
+  PromptParams pp;
+  pp.gauss = e->gauss; pp.point_emb = e->point_emb; pp.not_a_point = e->not_a_point;
+  pp.iou_token = e->iou_token; pp.mask_tokens = e->mask_tokens;
+  pp.points = points; pp.labels = labels; pp.boxes = boxes; pp.NP = points ? NP : 0; pp.pad = pad; pp.T = T;
+  pp.tokens = e->d_tok0;
+  prompt_tokens_kernel<<<B, 128, 0, st>>>(pp);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+
+  // image-side layer-0 operands: shared across prompts unless a mask prompt makes src per-prompt
+  const float *K0 = e->K0, *V0 = e->V0, *Qi0 = e->Qi0, *src = e->src0;
+  size_t kv_stride = 0;
+  int src_mod = 4096;
+  if (mask_in) {
+    MaskEmbedParams mp{mask_in, e->md_w0, e->md_b0, e->md_g1, e->md_be1, e->md_w3, e->md_b3, e->md_g4, e->md_be4, e->md_w6, e->md_b6,
+                       e->feat_tok, e->d_src};
+    mask_embed_src_kernel<<<(B * 4096 + 127) / 128, 128, 0, st>>>(mp, B);
+    SAMRS_CUDA_OK(cudaGetLastError());
+    count_launch();
+    const DecLayer& L0 = e->dl[0];
+    SAMRS_TRY(sgemm(st, e->d_src, 256, L0.t2i.wk, 256, e->d_Kp, 128, L0.t2i.bk, e->pek[0], 128, 4096, B * 4096, 128, 256, 0));
+    SAMRS_TRY(sgemm(st, e->d_src, 256, L0.t2i.wv, 256, e->d_Vp, 128, L0.t2i.bv, nullptr, 0, 0, B * 4096, 128, 256, 0));
+    SAMRS_TRY(sgemm(st, e->d_src, 256, L0.i2t.wq, 256, e->d_Qp, 128, L0.i2t.bq, e->pek[1], 128, 4096, B * 4096, 128, 256, 0));
+    K0 = e->d_Kp; V0 = e->d_Vp; Qi0 = e->d_Qp; src = e->d_src;
+    kv_stride = size_t(4096) * 128;
+    src_mod = 0;
+  }
+
+  float* queries = e->d_q;
+  float* qpl = e->d_tmp256d;          // queries + query_pe (scratch; token_attention uses a..d before we need it again)
+  for (int layer = 0; layer < 2; ++layer) {
+    const DecLayer& L = e->dl[layer];
+    // (1) token self-attention (transformer.py:155-161)
+    if (layer == 0) {
+      SAMRS_TRY(token_attention(e, st, L.self_attn, e->d_tok0, e->d_tok0, e->d_tok0, BT, T, B, queries, nullptr));
+    } else {
+      // q = k = queries + pe, v = queries, residual
+      float* qpe = e->d_mlp;            // reuse the MLP scratch as a [BT,256] temporary
+      SAMRS_TRY(add2(st, queries, e->d_tok0, qpe, size_t(BT) * 256));
+      SAMRS_TRY(token_attention(e, st, L.self_attn, qpe, qpe, queries, BT, T, B, queries, queries));
+    }
+    SAMRS_TRY((ln_rows<float, 0>(st, queries, 256, L.n1w, L.n1b, 1e-5f, queries, 256, BT, 256)));
+    // (2) tokens -> image (transformer.py:164-168)
+    SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
+    SAMRS_TRY(sgemm(st, qpl, 256, L.t2i.wq, 256, e->d_tmp128a, 128, L.t2i.bq, nullptr, 0, 0, BT, 128, 256, 0));
+    const float *Kl = K0, *Vl = V0;
+    size_t kvs = kv_stride;
+    if (layer == 1) {
+      SAMRS_TRY(sgemm(st, e->d_keys, 256, L.t2i.wk, 256, e->d_Kp, 128, L.t2i.bk, e->pek[2], 128, 4096, B * 4096, 128, 256, 0));
+      SAMRS_TRY(sgemm(st, e->d_keys, 256, L.t2i.wv, 256, e->d_Vp, 128, L.t2i.bv, nullptr, 0, 0, B * 4096, 128, 256, 0));
+      Kl = e->d_Kp; Vl = e->d_Vp; kvs = size_t(4096) * 128;
+    }
+    t2i_attn_kernel<<<dim3(B, 8), 256, 0, st>>>(e->d_tmp128a, Kl, Vl, kvs, e->d_tmp128b, T);
+    SAMRS_CUDA_OK(cudaGetLastError());
+    count_launch();
+    SAMRS_TRY(sgemm(st, e->d_tmp128b, 128, L.t2i.wo, 128, queries, 256, L.t2i.bo, queries, 256, 0, BT, 256, 128, 0));
+    SAMRS_TRY((ln_rows<float, 0>(st, queries, 256, L.n2w, L.n2b, 1e-5f, queries, 256, BT, 256)));
+    // (3) token MLP (transformer.py:171-173)
+    SAMRS_TRY(sgemm(st, queries, 256, L.m1w, 256, e->d_mlp, 2048, L.m1b, nullptr, 0, 0, BT, 2048, 256, 1));
+    SAMRS_TRY(sgemm(st, e->d_mlp, 2048, L.m2w, 2048, queries, 256, L.m2b, queries, 256, 0, BT, 256, 2048, 0));
+    SAMRS_TRY((ln_rows<float, 0>(st, queries, 256, L.n3w, L.n3b, 1e-5f, queries, 256, BT, 256)));
+    // (4) image -> tokens (transformer.py:176-180)
+    SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
+    SAMRS_TRY(sgemm(st, qpl, 256, L.i2t.wk, 256, e->d_tmp128a, 128, L.i2t.bk, nullptr, 0, 0, BT, 128, 256, 0));
+    SAMRS_TRY(sgemm(st, queries, 256, L.i2t.wv, 256, e->d_tmp128b, 128, L.i2t.bv, nullptr, 0, 0, BT, 128, 256, 0));
+    const float* Ql = Qi0;
+    size_t qs = kv_stride;
+    if (layer == 1) {
+      SAMRS_TRY(sgemm(st, e->d_keys, 256, L.i2t.wq, 256, e->d_Qp, 128, L.i2t.bq, e->pek[3], 128, 4096, B * 4096, 128, 256, 0));
+      Ql = e->d_Qp; qs = size_t(4096) * 128;
+    }
+    i2t_attn_kernel<<<dim3(4096 * 8 / 256, B), 256, size_t(2) * T * 128 * 4, st>>>(Ql, qs, e->d_tmp128a, e->d_tmp128b, e->d_io, T);
+    SAMRS_CUDA_OK(cudaGetLastError());
+    count_launch();
+    if (layer == 0)
+      SAMRS_TRY(sgemm(st, e->d_io, 128, L.i2t.wo, 128, e->d_keys, 256, L.i2t.bo, src, 256, src_mod, B * 4096, 256, 128, 0));
+    else
+      SAMRS_TRY(sgemm(st, e->d_io, 128, L.i2t.wo, 128, e->d_keys, 256, L.i2t.bo, e->d_keys, 256, 0, B * 4096, 256, 128, 0));
+    SAMRS_TRY((ln_rows<float, 0>(st, e->d_keys, 256, L.n4w, L.n4b, 1e-5f, e->d_keys, 256, B * 4096, 256)));
+  }
+  // final tokens -> image attention (transformer.py:99-104)
+  {
+    const DecAttn& a = e->final_attn;
+    SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
+    SAMRS_TRY(sgemm(st, qpl, 256, a.wq, 256, e->d_tmp128a, 128, a.bq, nullptr, 0, 0, BT, 128, 256, 0));
+    SAMRS_TRY(sgemm(st, e->d_keys, 256, a.wk, 256, e->d_Kp, 128, a.bk, e->pek[4], 128, 4096, B * 4096, 128, 256, 0));
+    SAMRS_TRY(sgemm(st, e->d_keys, 256, a.wv, 256, e->d_Vp, 128, a.bv, nullptr, 0, 0, B * 4096, 128, 256, 0));
+    t2i_attn_kernel<<<dim3(B, 8), 256, 0, st>>>(e->d_tmp128a, e->d_Kp, e->d_Vp, size_t(4096) * 128, e->d_tmp128b, T);
+    SAMRS_CUDA_OK(cudaGetLastError());
+    count_launch();
+    SAMRS_TRY(sgemm(st, e->d_tmp128b, 128, a.wo, 128, queries, 256, a.bo, queries, 256, 0, BT, 256, 128, 0));
+    SAMRS_TRY((ln_rows<float, 0>(st, queries, 256, e->nfw, e->nfb, 1e-5f, queries, 256, BT, 256)));
+  }
+  // hypernetwork MLPs on the needed mask tokens; IoU head on the iou token (mask_decoder.py:150-172)
+  const int NM = multimask ? 3 : 1, m_first = multimask ? 1 : 0;
+  for (int j = 0; j < NM; ++j) {
+    const Mlp3& h = e->hyper[m_first + j];
+    gather_token_kernel<<<(B * 256 + 255) / 256, 256, 0, st>>>(queries, T, 1 + m_first + j, e->d_hy_t, B);
+    SAMRS_CUDA_OK(cudaGetLastError());
+    count_launch();
+    SAMRS_TRY(sgemm(st, e->d_hy_t, 256, h.w[0], 256, e->d_hy_a, 256, h.b[0], nullptr, 0, 0, B, 256, 256, 1));
+    SAMRS_TRY(sgemm(st, e->d_hy_a, 256, h.w[1], 256, e->d_hy_b, 256, h.b[1], nullptr, 0, 0, B, 256, 256, 1));
+    SAMRS_TRY(sgemm(st, e->d_hy_b, 256, h.w[2], 256, e->d_hyper + j * 32, NM * 32, h.b[2], nullptr, 0, 0, B, 32, 256, 0));
+  }
+  gather_token_kernel<<<(B * 256 + 255) / 256, 256, 0, st>>>(queries, T, 0, e->d_hy_t, B);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  SAMRS_TRY(sgemm(st, e->d_hy_t, 256, e->iou_head.w[0], 256, e->d_hy_a, 256, e->iou_head.b[0], nullptr, 0, 0, B, 256, 256, 1));
+  SAMRS_TRY(sgemm(st, e->d_hy_a, 256, e->iou_head.w[1], 256, e->d_hy_b, 256, e->iou_head.b[1], nullptr, 0, 0, B, 256, 256, 1));
+  // last layer restricted to the returned slice: rows m_first .. m_first+NM-1 of the (4,256) weight
+  SAMRS_TRY(sgemm(st, e->d_hy_b, 256, e->iou_head.w[2] + m_first * 256, 256, iou_out, NM, e->iou_head.b[2] + m_first, nullptr, 0, 0, B, NM,
+                  256, 0));
+  // upscaling: ConvT1 as GEMM -> LN2d+GELU on 64-channel rows -> fused ConvT2+GELU+hyper product
+  SAMRS_TRY(sgemm(st, e->d_keys, 256, e->up_w1r, 256, e->d_u1, 256, e->up_b1r, nullptr, 0, 0, B * 4096, 256, 256, 0));
+  SAMRS_TRY((ln_rows<float, 1>(st, e->d_u1, 64, e->up_lnw, e->up_lnb, 1e-6f, e->d_u1, 64, B * 16384, 64)));
+  const unsigned ublocks = unsigned((size_t(B) * 16384 + 127) / 128);
+  if (NM == 1) upscale2_hyper_kernel<1><<<ublocks, 128, 0, st>>>(e->d_u1, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
+  else upscale2_hyper_kernel<3><<<ublocks, 128, 0, st>>>(e->d_u1, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace samrs
+
+// ====================================================================== C ABI
+using namespace samrs;
+
+struct LaunchScope {
+  explicit LaunchScope(Engine* e) { g_launch_counter = e ? &e->launches : nullptr; }
+  ~LaunchScope() { g_launch_counter = nullptr; }
+};
+
+extern "C" {
+
+int samrs_create(int device, int embed_dim, int depth, int num_heads, const int* global_idx, int n_global, void** out) {
+  if (!out) return 1;
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return samrs::fail(__FILE__, __LINE__, "no CUDA device: samrs_b200 has no CPU path");
+  if (device < 0 || device >= ndev) return samrs::fail(__FILE__, __LINE__, "bad device index");
+  if (embed_dim % num_heads != 0) return samrs::fail(__FILE__, __LINE__, "embed_dim must be divisible by num_heads");
+  const int hd = embed_dim / num_heads;
+  if (hd != 64 && hd != 80) return samrs::fail(__FILE__, __LINE__, "head_dim must be 64 or 80");
+  if (embed_dim % 32 != 0 || embed_dim > 1280) return samrs::fail(__FILE__, __LINE__, "embed_dim must be a multiple of 32, at most 1280");
+  cudaDeviceProp prop;
+  if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess)
+    return samrs::fail(__FILE__, __LINE__, "cudaSetDevice failed");
+  if (prop.major != 10) return samrs::fail(__FILE__, __LINE__, "samrs_b200 requires an sm_100 (Blackwell) GPU");
+  Engine* e = new Engine();
+  e->device = device;
+  e->D = embed_dim; e->depth = depth; e->heads = num_heads; e->hd = hd;
+  e->global_idx.assign(global_idx, global_idx + n_global);
+  e->num_sms = prop.multiProcessorCount;
+  if (alloc_activations(e) != 0) {
+    samrs_destroy(e);
+    return 1;
+  }
+  *out = e;
+  return 0;
+}
+
+int samrs_load_weights(void* engine, int n, const char* const* names, const void* const* dev_ptrs, const int64_t* numel, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  SrcMap m;
+  for (int i = 0; i < n; ++i) m[names[i]] = Src{static_cast<const float*>(dev_ptrs[i]), numel[i]};
+  LaunchScope ls(nullptr);
+  int rc = load_weights_impl(e, m, static_cast<cudaStream_t>(stream));
+  if (rc == 0) e->weights_loaded = true;
+  return set_err(e, rc);
+}
+
+int samrs_encode(void* engine, const uint8_t* img, int H, int W, int chw, float* features_out, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  return set_err(e, encode_impl(e, img, H, W, chw, features_out, static_cast<cudaStream_t>(stream)));
+}
+
+int samrs_set_features(void* engine, const float* features, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!e->weights_loaded) return set_err(e, samrs::fail(__FILE__, __LINE__, "set_features: weights not loaded"));
+  transpose_nchw_to_tok_kernel<<<dim3(128, 8), dim3(32, 8), 0, st>>>(features, e->feat_tok, 256);
+  count_launch();
+  return set_err(e, build_image_cache(e, st));
+}
+
+int samrs_decode(void* engine, const float* boxes, const float* points, const int* labels, int NP, const float* mask_in, int B,
+                 int multimask, float* lowres_out, float* iou_out, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  if (!e->image_set) return set_err(e, samrs::fail(__FILE__, __LINE__, "An image must be set with .set_image(...) before mask prediction."));
+  if (B < 1) return set_err(e, samrs::fail(__FILE__, __LINE__, "decode: B must be >= 1"));
+  if (points && !labels) return set_err(e, samrs::fail(__FILE__, __LINE__, "decode: point labels missing"));
+  const int C = multimask ? 3 : 1;
+  const int CH = 64;     // prompts per pass (bounds scratch at ~1.3 GB)
+  for (int b0 = 0; b0 < B; b0 += CH) {
+    const int nb = (B - b0 < CH) ? (B - b0) : CH;
+    int rc = decode_chunk(e, static_cast<cudaStream_t>(stream), boxes ? boxes + size_t(b0) * 4 : nullptr,
+                          points ? points + size_t(b0) * NP * 2 : nullptr, labels ? labels + size_t(b0) * NP : nullptr, NP,
+                          mask_in ? mask_in + size_t(b0) * 65536 : nullptr, nb, multimask, lowres_out + size_t(b0) * C * 65536,
+                          iou_out + size_t(b0) * C);
+    if (rc != 0) return set_err(e, rc);
+  }
+  return 0;
+}
+
+int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int in_w, int out_h, int out_w, uint8_t* masks_out,
+                      float* logits_out, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (NB < 1) return 0;
+  if (in_h == 1024 && in_w == 1024 && out_h == 1024 && out_w == 1024) {
+    for (int b0 = 0; b0 < NB; b0 += 32768) {
+      const int nb = NB - b0 < 32768 ? NB - b0 : 32768;
+      upsample4_threshold_kernel<<<dim3(1, 1024, nb), 256, 0, st>>>(lowres + size_t(b0) * 65536, masks_out ? masks_out + size_t(b0) * 1048576 : nullptr,
+                                                                    logits_out ? logits_out + size_t(b0) * 1048576 : nullptr, nb);
+    }
+    count_launch();
+    if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "postprocess launch failed"));
+    return 0;
+  }
+  // general sizes: 256 -> 1024 (fp32 scratch), crop, -> (out_h, out_w)
+  const int CH = 16;
+  if (!e->pp_full && e->alloc(&e->pp_full, size_t(CH) * 1048576) != 0) return set_err(e, 1);
+  float* full = e->pp_full;
+  for (int b0 = 0; b0 < NB; b0 += CH) {
+    const int nb = NB - b0 < CH ? NB - b0 : CH;
+    bilinear_resize_kernel<<<dim3(4, 1024, nb), 256, 0, st>>>(lowres + size_t(b0) * 65536, 256, 65536, 256, 256, full, nullptr, 1024, 1024, nb);
+    bilinear_resize_kernel<<<dim3((out_w + 255) / 256, out_h, nb), 256, 0, st>>>(
+        full, 1024, 1048576, in_h, in_w, logits_out ? logits_out + size_t(b0) * out_h * out_w : nullptr,
+        masks_out ? masks_out + size_t(b0) * out_h * out_w : nullptr, out_h, out_w, nb);
+    count_launch(2);
+  }
+  if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "postprocess launch failed"));
+  return 0;
+}
+
+int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_ids, int B, uint8_t* label_map, int H, int W, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  if (H != 1024 || W != 1024) return set_err(e, samrs::fail(__FILE__, __LINE__, "semantic_reduce: only 1024x1024 tiles are supported"));
+  if (B < 1) return 0;
+  upsample4_paint_kernel<<<dim3(1, 1024), 256, 0, static_cast<cudaStream_t>(stream)>>>(lowres, class_ids, B, label_map);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "semantic_reduce launch failed"));
+  return 0;
+}
+
+int samrs_launch_count(void* engine, int64_t* out) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e || !out) return 1;
+  *out = e->launches;
+  return 0;
+}
+
+const char* samrs_last_error(void* engine) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (e && !e->err.empty()) return e->err.c_str();
+  return g_last_error.c_str();
+}
+
+void samrs_destroy(void* engine) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return;
+  cudaSetDevice(e->device);
+  for (void* p : e->allocs) cudaFree(p);
+  delete e;
+}
+
+int samrs_test_gemm(void* engine, const void* A, const void* B, int M, int N, int K, void* out, int out_half, const float* bias,
+                    const float* res, int act_gelu, int force_bn, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.out = out; p.ldc = N; p.bias = bias; p.res = res; p.ldr = N; p.res_mod = 0; p.tiles_m = p.tiles_n = 0;
+  return set_err(e, launch_gemm_tc(static_cast<const __half*>(A), K, static_cast<const __half*>(B), K, p, out_half != 0, act_gelu, e->num_sms,
+                                   static_cast<cudaStream_t>(stream), force_bn));
+}
+
+int samrs_test_attention(void* engine, const void* qkv, const float* rph, const float* rpw, int global_block, void* out, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  return set_err(e, encoder_attention(e, static_cast<cudaStream_t>(stream), static_cast<const __half*>(qkv), rph, rpw, global_block != 0,
+                                      static_cast<__half*>(out)));
+}
+
+int samrs_test_sgemm(void* engine, const float* A, const float* W, float* C, const float* bias, int M, int N, int K, int act, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  return set_err(e, sgemm(static_cast<cudaStream_t>(stream), A, K, W, K, C, N, bias, nullptr, 0, 0, M, N, K, act));
+}
+
+}  // extern "C"

@@ -1,0 +1,759 @@
+// CUDA-core kernels of the samrs_b200 engine: everything on the SAM path that is not a large GEMM /
+// attention contraction.  All are HBM- or latency-bound; layouts are chosen so that every warp reads
+// and writes contiguous 128-byte lines.
+#pragma once
+#include "common.cuh"
+
+namespace samrs {
+
+__device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+// ------------------------------------------------------------------------------------------------
+// Sam.preprocess (SA/modeling/sam.py:164-174) fused with the patch gather of PatchEmbed's 16x16/s16 conv
+// (SA/modeling/image_encoder.py:391-395): u8 HWC image -> A[4096][768] fp16, k = c*256 + iy*16 + ix.
+// Pixels outside (H,W) are the zero padding applied after normalisation.
+// ------------------------------------------------------------------------------------------------
+__global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, int H, int W, int chw /*1: CHW input*/,
+                                         __half* __restrict__ A) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;     // one thread per (patch, c, iy), 16 ix each
+  if (idx >= 4096 * 48) return;
+  const int patch = idx / 48, rem = idx % 48, c = rem / 16, iy = rem % 16;
+  const int py = patch / 64, px = patch % 64;
+  const int y = py * 16 + iy;
+  const float mean = (c == 0) ? 123.675f : (c == 1 ? 116.28f : 103.53f);
+  const float sd = (c == 0) ? 58.395f : (c == 1 ? 57.12f : 57.375f);
+  __half vals[16];
+#pragma unroll
+  for (int ix = 0; ix < 16; ++ix) {
+    const int x = px * 16 + ix;
+    float v = 0.f;
+    if (y < H && x < W) {
+      const uint8_t u = chw ? img[(size_t(c) * H + y) * W + x] : img[(size_t(y) * W + x) * 3 + c];
+      v = __fdiv_rn(__fsub_rn(float(u), mean), sd);
+    }
+    vals[ix] = __float2half_rn(v);
+  }
+  uint4* dst = reinterpret_cast<uint4*>(A + size_t(patch) * 768 + c * 256 + iy * 16);
+  dst[0] = *reinterpret_cast<uint4*>(&vals[0]);
+  dst[1] = *reinterpret_cast<uint4*>(&vals[8]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Row LayerNorm (nn.LayerNorm / LayerNorm2d over a contiguous channel row): one warp per row,
+// two-pass mean / biased variance in registers.  OutT = __half feeds the next tensor-core GEMM,
+// OutT = float is used by the decoder.  ACT 1 = GELU(erf) (output_upscaling, mask_downscaling).
+// ------------------------------------------------------------------------------------------------
+template <typename OutT, int ACT, int MAXV /* float4 per lane */>
+__global__ void ln_rows_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, float eps, OutT* __restrict__ out, int ld_out,
+                               int rows, int C) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(in + size_t(warp) * ld_in);
+  const int nv = C >> 2;
+  float4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int k = lane + 32 * i;
+    v[i] = (k < nv) ? src[k] : make_float4(0, 0, 0, 0);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / float(C);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int k = lane + 32 * i;
+    if (k < nv) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / float(C) + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int k = lane + 32 * i;
+    if (k < nv) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + k);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + k);
+      float y0 = (v[i].x - mean) * rstd * g.x + b.x;
+      float y1 = (v[i].y - mean) * rstd * g.y + b.y;
+      float y2 = (v[i].z - mean) * rstd * g.z + b.z;
+      float y3 = (v[i].w - mean) * rstd * g.w + b.w;
+      if (ACT == 1) { y0 = gelu_erf_f(y0); y1 = gelu_erf_f(y1); y2 = gelu_erf_f(y2); y3 = gelu_erf_f(y3); }
+      if (sizeof(OutT) == 2) {
+        __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+        uint2 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0);
+        pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        reinterpret_cast<uint2*>(reinterpret_cast<__half*>(out) + size_t(warp) * ld_out)[k] = pk;
+      } else {
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(out) + size_t(warp) * ld_out)[k] = make_float4(y0, y1, y2, y3);
+      }
+    }
+  }
+}
+
+// fp32 -> fp16 cast of a contiguous buffer (n multiple of 4)
+__global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n4) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(in)[i];
+  __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
+  uint2 pk;
+  pk.x = *reinterpret_cast<uint32_t*>(&h0);
+  pk.y = *reinterpret_cast<uint32_t*>(&h1);
+  reinterpret_cast<uint2*>(out)[i] = pk;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decomposed relative-position terms (SA/modeling/image_encoder.py:325-361, get_rel_pos :292-322):
+//   rel_h[q, kh] = q . rel_pos_h[qh - kh + S - 1],  rel_w[q, kw] = q . rel_pos_w[qw - kw + S - 1]
+// with the UNSCALED q, S = 14 (window-local coordinates) or 64 (global).
+// Output: rel[head][token][2*S] fp32, pre-multiplied by log2(e) for the exp2-domain softmax.
+// One block per (8 tokens, head); the two tables are staged in shared memory with a +1 row pad.
+// ------------------------------------------------------------------------------------------------
+template <int HD>
+__global__ void relpos_kernel(const __half* __restrict__ qkv, int ld_qkv, const float* __restrict__ rph,
+                              const float* __restrict__ rpw, int S, float* __restrict__ rel) {
+  extern __shared__ float sm[];
+  constexpr int TOK = 8;
+  const int L = 2 * S - 1;
+  float* th = sm;                    // [L][HD+1]
+  float* tw = th + L * (HD + 1);     // [L][HD+1]
+  float* sq = tw + L * (HD + 1);     // [TOK][HD]
+  const int head = blockIdx.y;
+  const int tok0 = blockIdx.x * TOK;
+  for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
+    th[(i / HD) * (HD + 1) + i % HD] = rph[i];
+    tw[(i / HD) * (HD + 1) + i % HD] = rpw[i];
+  }
+  for (int i = threadIdx.x; i < TOK * HD; i += blockDim.x)
+    sq[i] = __half2float(qkv[size_t(tok0 + i / HD) * ld_qkv + head * HD + i % HD]);
+  __syncthreads();
+  const float LOG2E = 1.4426950408889634f;
+  for (int o = threadIdx.x; o < TOK * 2 * S; o += blockDim.x) {
+    const int t = o / (2 * S), j = o % (2 * S);
+    const int token = tok0 + t;
+    const int y = token >> 6, x = token & 63;
+    const int qh = (S == 64) ? y : (y % 14), qw = (S == 64) ? x : (x % 14);
+    const float* tab = (j < S) ? th + (qh - j + S - 1) * (HD + 1) : tw + (qw - (j - S) + S - 1) * (HD + 1);
+    const float* qv = sq + t * HD;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int c = 0; c < HD; ++c) acc = fmaf(qv[c], tab[c], acc);
+    rel[(size_t(head) * 4096 + token) * (2 * S) + j] = acc * LOG2E;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Neck helpers (SA/modeling/image_encoder.py:88-104): 3x3/pad-1 conv as im2col'ed GEMM, and the final
+// LayerNorm2d written both token-major (decoder input) and NCHW (the `features` tensor of the API).
+// ------------------------------------------------------------------------------------------------
+__global__ void neck_im2col3x3_kernel(const __half* __restrict__ in /*[4096][256]*/, __half* __restrict__ out /*[4096][2304]*/) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // one thread per (token, tap, 8-channel chunk)
+  if (idx >= 4096 * 9 * 32) return;
+  const int chunk = idx & 31, tap = (idx >> 5) % 9, token = idx / (9 * 32);
+  const int y = (token >> 6) + tap / 3 - 1, x = (token & 63) + tap % 3 - 1;
+  uint4 v = make_uint4(0, 0, 0, 0);
+  if (y >= 0 && y < 64 && x >= 0 && x < 64) v = reinterpret_cast<const uint4*>(in + size_t(y * 64 + x) * 256)[chunk];
+  reinterpret_cast<uint4*>(out + size_t(token) * 2304 + tap * 256)[chunk] = v;
+}
+
+__global__ void transpose_tok_to_nchw_kernel(const float* __restrict__ in /*[4096][C]*/, float* __restrict__ out /*[C][4096]*/, int C) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = in[size_t(t0 + i) * C + c0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) out[size_t(c0 + i) * 4096 + t0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+__global__ void transpose_nchw_to_tok_kernel(const float* __restrict__ in /*[C][4096]*/, float* __restrict__ out /*[4096][C]*/, int C) {
+  __shared__ float tile[32][33];
+  const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) tile[i][threadIdx.x] = in[size_t(c0 + i) * 4096 + t0 + threadIdx.x];
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) out[size_t(t0 + i) * C + c0 + threadIdx.x] = tile[threadIdx.x][i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 SGEMM for the mask decoder (precision-sensitive, 2 % of the FLOPs):
+//   C[M,N] = act(A[M,K] W[N,K]^T + bias[N] + R[m % rmod][N])      K % 16 == 0
+// 128x64 block tile, 16-deep k slices, 8x4 outputs per thread, operands transposed into smem.
+// ------------------------------------------------------------------------------------------------
+struct SgemmParams {
+  const float* A; int lda;
+  const float* W; int ldw;
+  float* C; int ldc;
+  const float* bias;
+  const float* R; int ldr; int rmod;
+  int M, N, K;
+  int act;              // 0 none, 1 relu, 2 gelu
+};
+
+__global__ void __launch_bounds__(256)
+sgemm_tn_kernel(const SgemmParams p) {
+  __shared__ __align__(16) float As[2][16][128 + 4];
+  __shared__ __align__(16) float Ws[2][16][64 + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * 128, n0 = blockIdx.y * 64;
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  // global->register staging: A tile 128x16 = 512 float4 (2 per thread), W tile 64x16 = 256 float4 (1 per thread)
+  const int a_row0 = tid / 4, a_k4 = (tid % 4) * 4;            // rows a_row0 and a_row0 + 64
+  const int w_row = tid / 4, w_k4 = (tid % 4) * 4;
+  float4 ra0, ra1, rw;
+  auto gload = [&](int k0) {
+    const int r0 = m0 + a_row0, r1 = r0 + 64;
+    ra0 = (r0 < p.M) ? *reinterpret_cast<const float4*>(p.A + size_t(r0) * p.lda + k0 + a_k4) : make_float4(0, 0, 0, 0);
+    ra1 = (r1 < p.M) ? *reinterpret_cast<const float4*>(p.A + size_t(r1) * p.lda + k0 + a_k4) : make_float4(0, 0, 0, 0);
+    const int wr = n0 + w_row;
+    rw = (wr < p.N) ? *reinterpret_cast<const float4*>(p.W + size_t(wr) * p.ldw + k0 + w_k4) : make_float4(0, 0, 0, 0);
+  };
+  auto sstore = [&](int buf) {
+    As[buf][a_k4 + 0][a_row0] = ra0.x; As[buf][a_k4 + 1][a_row0] = ra0.y; As[buf][a_k4 + 2][a_row0] = ra0.z; As[buf][a_k4 + 3][a_row0] = ra0.w;
+    As[buf][a_k4 + 0][a_row0 + 64] = ra1.x; As[buf][a_k4 + 1][a_row0 + 64] = ra1.y; As[buf][a_k4 + 2][a_row0 + 64] = ra1.z; As[buf][a_k4 + 3][a_row0 + 64] = ra1.w;
+    Ws[buf][w_k4 + 0][w_row] = rw.x; Ws[buf][w_k4 + 1][w_row] = rw.y; Ws[buf][w_k4 + 2][w_row] = rw.z; Ws[buf][w_k4 + 3][w_row] = rw.w;
+  };
+  gload(0);
+  sstore(0);
+  __syncthreads();
+  const int nk = p.K / 16;
+  for (int kb = 0; kb < nk; ++kb) {
+    const int buf = kb & 1;
+    if (kb + 1 < nk) gload((kb + 1) * 16);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 8 + 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[buf][k][tx * 4]);
+      const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float b[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    if (kb + 1 < nk) {
+      sstore(buf ^ 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
+    if (m >= p.M) continue;
+    const float* rrow = p.R ? p.R + size_t(p.rmod > 0 ? m % p.rmod : m) * p.ldr : nullptr;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.bias) v += __ldg(p.bias + n);
+      if (rrow) v += rrow[n];
+      if (p.act == 1) v = fmaxf(v, 0.f);
+      else if (p.act == 2) v = gelu_erf_f(v);
+      p.C[size_t(m) * p.ldc + n] = v;
+    }
+  }
+}
+
+// out[r][c] = a[r % amod][c] + b[c] (+ r-indexed table)   -- small broadcast adds used by the decoder set-up
+__global__ void add_rowvec_kernel(const float* __restrict__ a, int amod, const float* __restrict__ vec, float* __restrict__ out,
+                                  int rows, int C) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= size_t(rows) * C) return;
+  const int r = int(i / C), c = int(i % C);
+  out[i] = a[size_t(amod > 0 ? r % amod : r) * C + c] + (vec ? vec[c] : 0.f);
+}
+__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, size_t n) {
+  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i < n) a[i] += b[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Prompt encoder (SA/modeling/prompt_encoder.py:73-100,128-173,190-219) + decoder token assembly
+// (SA/modeling/mask_decoder.py:127-129).  tokens[b] = [iou, mask0..3, points..., (pad), box corners].
+// One block per prompt, one thread per channel pair (sin at c, cos at c + 128).
+// ------------------------------------------------------------------------------------------------
+struct PromptParams {
+  const float* gauss;          // [2][128]
+  const float* point_emb;      // [4][256]
+  const float* not_a_point;    // [256]
+  const float* iou_token;      // [256]
+  const float* mask_tokens;    // [4][256]
+  const float* points;         // [B][NP][2] or null
+  const int* labels;           // [B][NP]
+  const float* boxes;          // [B][4] or null
+  int NP;                      // points per prompt (without pad)
+  int pad;                     // append the (0,0)/-1 pad point (points given, no boxes)
+  int T;                       // tokens per prompt
+  float* tokens;               // [B][T][256]
+};
+
+__device__ __forceinline__ void pe_pair(const float* gauss, float x, float y, int c, float& s, float& co) {
+  // forward_with_coords (:212-219) -> _pe_encoding (:190-197): coords already include the +0.5 shift
+  float cx = x / 1024.0f, cy = y / 1024.0f;
+  cx = 2.0f * cx - 1.0f;
+  cy = 2.0f * cy - 1.0f;
+  float v = __fadd_rn(__fmul_rn(cx, gauss[c]), __fmul_rn(cy, gauss[128 + c]));
+  v = 6.283185307179586f * v;
+  s = sinf(v);
+  co = cosf(v);
+}
+
+__global__ void prompt_tokens_kernel(const PromptParams p) {
+  const int b = blockIdx.x, c = threadIdx.x;     // 128 threads
+  float* tok = p.tokens + size_t(b) * p.T * 256;
+  tok[c] = p.iou_token[c];
+  tok[c + 128] = p.iou_token[c + 128];
+  for (int i = 0; i < 4; ++i) {
+    tok[(1 + i) * 256 + c] = p.mask_tokens[i * 256 + c];
+    tok[(1 + i) * 256 + c + 128] = p.mask_tokens[i * 256 + c + 128];
+  }
+  int t = 5;
+  if (p.points) {
+    for (int i = 0; i < p.NP + p.pad; ++i, ++t) {
+      float x = 0.f, y = 0.f;
+      int lab = -1;
+      if (i < p.NP) {
+        x = p.points[(size_t(b) * p.NP + i) * 2 + 0];
+        y = p.points[(size_t(b) * p.NP + i) * 2 + 1];
+        lab = p.labels[size_t(b) * p.NP + i];
+      }
+      float s, co;
+      pe_pair(p.gauss, x + 0.5f, y + 0.5f, c, s, co);
+      if (lab == -1) { s = 0.f + p.not_a_point[c]; co = 0.f + p.not_a_point[c + 128]; }
+      else if (lab == 0) { s += p.point_emb[c]; co += p.point_emb[c + 128]; }
+      else if (lab == 1) { s += p.point_emb[256 + c]; co += p.point_emb[256 + c + 128]; }
+      tok[t * 256 + c] = s;
+      tok[t * 256 + c + 128] = co;
+    }
+  }
+  if (p.boxes) {
+    for (int i = 0; i < 2; ++i, ++t) {
+      const float x = p.boxes[size_t(b) * 4 + 2 * i], y = p.boxes[size_t(b) * 4 + 2 * i + 1];
+      float s, co;
+      pe_pair(p.gauss, x + 0.5f, y + 0.5f, c, s, co);
+      s += p.point_emb[(2 + i) * 256 + c];
+      co += p.point_emb[(2 + i) * 256 + c + 128];
+      tok[t * 256 + c] = s;
+      tok[t * 256 + c + 128] = co;
+    }
+  }
+}
+
+// get_dense_pe (:62-71,199-210): pe[token][c], token = y*64+x, coords ((x+0.5)/64, (y+0.5)/64)
+__global__ void dense_pe_kernel(const float* __restrict__ gauss, float* __restrict__ pe /*[4096][256]*/) {
+  const int token = blockIdx.x, c = threadIdx.x;   // 128 threads
+  const float fx = (float(token & 63) + 0.5f) / 64.0f, fy = (float(token >> 6) + 0.5f) / 64.0f;
+  const float cx = 2.0f * fx - 1.0f, cy = 2.0f * fy - 1.0f;
+  float v = __fadd_rn(__fmul_rn(cx, gauss[c]), __fmul_rn(cy, gauss[128 + c]));
+  v = 6.283185307179586f * v;
+  pe[size_t(token) * 256 + c] = sinf(v);
+  pe[size_t(token) * 256 + c + 128] = cosf(v);
+}
+
+// mask_downscaling (SA/modeling/prompt_encoder.py:51-59,102-105) fused with `src = features + dense`
+// (SA/modeling/mask_decoder.py:136-137): one thread per (prompt, token) -> src[b][token][0..255].
+struct MaskEmbedParams {
+  const float* mask;      // [B][256][256]
+  const float *w0, *b0, *g1, *be1, *w3, *b3, *g4, *be4, *w6, *b6;
+  const float* feat;      // [4096][256] token-major image embedding
+  float* src;             // [B][4096][256]
+};
+__global__ void mask_embed_src_kernel(const MaskEmbedParams p, int B) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= B * 4096) return;
+  const int b = idx / 4096, token = idx % 4096, ty = token >> 6, tx = token & 63;
+  const float* m = p.mask + size_t(b) * 65536;
+  float h2[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) h2[o] = p.b3[o];
+#pragma unroll
+  for (int py = 0; py < 2; ++py)
+#pragma unroll
+    for (int px = 0; px < 2; ++px) {
+      // conv0 (1->4, k2 s2) at 128x128 position (2ty+py, 2tx+px)
+      const int y0 = (2 * ty + py) * 2, x0 = (2 * tx + px) * 2;
+      const float i00 = m[y0 * 256 + x0], i01 = m[y0 * 256 + x0 + 1], i10 = m[(y0 + 1) * 256 + x0], i11 = m[(y0 + 1) * 256 + x0 + 1];
+      float h[4];
+      float mu = 0.f;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) {
+        h[o] = p.b0[o] + p.w0[o * 4 + 0] * i00 + p.w0[o * 4 + 1] * i01 + p.w0[o * 4 + 2] * i10 + p.w0[o * 4 + 3] * i11;
+        mu += h[o];
+      }
+      mu *= 0.25f;
+      float var = 0.f;
+#pragma unroll
+      for (int o = 0; o < 4; ++o) var += (h[o] - mu) * (h[o] - mu);
+      var *= 0.25f;
+      const float rs = 1.0f / sqrtf(var + 1e-6f);
+#pragma unroll
+      for (int o = 0; o < 4; ++o) h[o] = gelu_erf_f(p.g1[o] * ((h[o] - mu) * rs) + p.be1[o]);
+      // conv3 (4->16, k2 s2): weight [16][4][2][2]
+#pragma unroll
+      for (int o = 0; o < 16; ++o)
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) h2[o] += p.w3[((o * 4 + ci) * 2 + py) * 2 + px] * h[ci];
+    }
+  float mu = 0.f;
+#pragma unroll
+  for (int o = 0; o < 16; ++o) mu += h2[o];
+  mu *= (1.0f / 16.0f);
+  float var = 0.f;
+#pragma unroll
+  for (int o = 0; o < 16; ++o) var += (h2[o] - mu) * (h2[o] - mu);
+  var *= (1.0f / 16.0f);
+  const float rs = 1.0f / sqrtf(var + 1e-6f);
+#pragma unroll
+  for (int o = 0; o < 16; ++o) h2[o] = gelu_erf_f(p.g4[o] * ((h2[o] - mu) * rs) + p.be4[o]);
+  float* dst = p.src + (size_t(b) * 4096 + token) * 256;
+  const float* f = p.feat + size_t(token) * 256;
+  for (int c = 0; c < 256; ++c) {
+    float v = p.b6[c];
+#pragma unroll
+    for (int ci = 0; ci < 16; ++ci) v += p.w6[c * 16 + ci] * h2[ci];
+    dst[c] = f[c] + v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Decoder attention (SA/modeling/transformer.py:218-240), three shapes.
+// ------------------------------------------------------------------------------------------------
+// (1) token self-attention: q,k,v [B][T][256] already projected, 8 heads x 32.  One block per prompt.
+__global__ void tok_self_attn_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                                     float* __restrict__ out, int T) {
+  extern __shared__ float sm[];
+  float* sq = sm;
+  float* sk = sq + T * 256;
+  float* sv = sk + T * 256;
+  float* sc = sv + T * 256;               // [8][T][T]
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < T * 256; i += blockDim.x) {
+    sq[i] = q[size_t(b) * T * 256 + i];
+    sk[i] = k[size_t(b) * T * 256 + i];
+    sv[i] = v[size_t(b) * T * 256 + i];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * T * T; i += blockDim.x) {
+    const int h = i / (T * T), tq = (i / T) % T, tk = i % T;
+    float s = 0.f;
+    for (int c = 0; c < 32; ++c) s = fmaf(sq[tq * 256 + h * 32 + c], sk[tk * 256 + h * 32 + c], s);
+    sc[i] = s / sqrtf(32.0f);
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 8 * T; i += blockDim.x) {
+    float* row = sc + i * T;
+    float mx = -INFINITY;
+    for (int j = 0; j < T; ++j) mx = fmaxf(mx, row[j]);
+    float sum = 0.f;
+    for (int j = 0; j < T; ++j) { row[j] = expf(row[j] - mx); sum += row[j]; }
+    for (int j = 0; j < T; ++j) row[j] /= sum;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < T * 256; i += blockDim.x) {
+    const int tq = i / 256, ch = i % 256, h = ch / 32;
+    float acc = 0.f;
+    for (int j = 0; j < T; ++j) acc = fmaf(sc[(h * T + tq) * T + j], sv[j * 256 + ch], acc);
+    out[size_t(b) * T * 256 + i] = acc;
+  }
+}
+
+// (2) token -> image cross attention: q [B][T][128]; K,V [B or 1][4096][128] (kv_bstride 0 = shared);
+//     8 heads x 16.  One block per (prompt, head), 256 threads x 16 keys each, softmax over 4096 keys.
+__global__ void __launch_bounds__(256)
+t2i_attn_kernel(const float* __restrict__ q, const float* __restrict__ K, const float* __restrict__ V,
+                size_t kv_bstride, float* __restrict__ out, int T) {
+  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const float* Kb = K + size_t(b) * kv_bstride + h * 16;
+  const float* Vb = V + size_t(b) * kv_bstride + h * 16;
+  __shared__ float red[8][18];
+  for (int t = 0; t < T; ++t) {
+    float qv[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) qv[c] = q[(size_t(b) * T + t) * 128 + h * 16 + c];
+    float s[16];
+    float m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float4* kr = reinterpret_cast<const float4*>(Kb + size_t(tid + 256 * i) * 128);
+      const float4 k0 = kr[0], k1 = kr[1], k2 = kr[2], k3 = kr[3];
+      float a = qv[0] * k0.x;
+      a = fmaf(qv[1], k0.y, a); a = fmaf(qv[2], k0.z, a); a = fmaf(qv[3], k0.w, a);
+      a = fmaf(qv[4], k1.x, a); a = fmaf(qv[5], k1.y, a); a = fmaf(qv[6], k1.z, a); a = fmaf(qv[7], k1.w, a);
+      a = fmaf(qv[8], k2.x, a); a = fmaf(qv[9], k2.y, a); a = fmaf(qv[10], k2.z, a); a = fmaf(qv[11], k2.w, a);
+      a = fmaf(qv[12], k3.x, a); a = fmaf(qv[13], k3.y, a); a = fmaf(qv[14], k3.z, a); a = fmaf(qv[15], k3.w, a);
+      s[i] = a * 0.25f;                     // / sqrt(16)
+      m = fmaxf(m, s[i]);
+    }
+    // block max
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5][0] = m;
+    __syncthreads();
+    m = red[0][0];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w][0]);
+    __syncthreads();
+    float l = 0.f;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float pexp = expf(s[i] - m);
+      l += pexp;
+      const float4* vr = reinterpret_cast<const float4*>(Vb + size_t(tid + 256 * i) * 128);
+      const float4 v0 = vr[0], v1 = vr[1], v2 = vr[2], v3 = vr[3];
+      acc[0] = fmaf(pexp, v0.x, acc[0]); acc[1] = fmaf(pexp, v0.y, acc[1]); acc[2] = fmaf(pexp, v0.z, acc[2]); acc[3] = fmaf(pexp, v0.w, acc[3]);
+      acc[4] = fmaf(pexp, v1.x, acc[4]); acc[5] = fmaf(pexp, v1.y, acc[5]); acc[6] = fmaf(pexp, v1.z, acc[6]); acc[7] = fmaf(pexp, v1.w, acc[7]);
+      acc[8] = fmaf(pexp, v2.x, acc[8]); acc[9] = fmaf(pexp, v2.y, acc[9]); acc[10] = fmaf(pexp, v2.z, acc[10]); acc[11] = fmaf(pexp, v2.w, acc[11]);
+      acc[12] = fmaf(pexp, v3.x, acc[12]); acc[13] = fmaf(pexp, v3.y, acc[13]); acc[14] = fmaf(pexp, v3.z, acc[14]); acc[15] = fmaf(pexp, v3.w, acc[15]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, o);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+    if ((tid & 31) == 0) {
+      red[tid >> 5][16] = l;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) red[tid >> 5][c] = acc[c];
+    }
+    __syncthreads();
+    if (tid < 16) {
+      float num = 0.f, den = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) { num += red[w][tid]; den += red[w][16]; }
+      out[(size_t(b) * T + t) * 128 + h * 16 + tid] = num / den;
+    }
+    __syncthreads();
+  }
+}
+
+// (3) image -> token cross attention: Q [B or 1][4096][128] (q_bstride 0 = shared); k,v [B][T][128];
+//     one thread per (prompt, image token, head); k,v of the prompt staged in smem.
+__global__ void __launch_bounds__(256)
+i2t_attn_kernel(const float* __restrict__ Q, size_t q_bstride, const float* __restrict__ k, const float* __restrict__ v,
+                float* __restrict__ out /*[B][4096][128]*/, int T) {
+  extern __shared__ float sm[];
+  float* sk = sm;
+  float* sv = sm + T * 128;
+  const int b = blockIdx.y;
+  for (int i = threadIdx.x; i < T * 128; i += blockDim.x) {
+    sk[i] = k[size_t(b) * T * 128 + i];
+    sv[i] = v[size_t(b) * T * 128 + i];
+  }
+  __syncthreads();
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (token, head)
+  if (idx >= 4096 * 8) return;
+  const int token = idx >> 3, h = idx & 7;
+  const float4* qr = reinterpret_cast<const float4*>(Q + size_t(b) * q_bstride + size_t(token) * 128 + h * 16);
+  const float4 q0 = qr[0], q1 = qr[1], q2 = qr[2], q3 = qr[3];
+  const float qv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+  float s[16];
+  float m = -INFINITY;
+  for (int t = 0; t < T; ++t) {
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) a = fmaf(qv[c], sk[t * 128 + h * 16 + c], a);
+    s[t] = a * 0.25f;
+    m = fmaxf(m, s[t]);
+  }
+  float l = 0.f;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float pexp = expf(s[t] - m);
+    l += pexp;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = fmaf(pexp, sv[t * 128 + h * 16 + c], acc[c]);
+  }
+  const float inv = 1.0f / l;
+  float4* o = reinterpret_cast<float4*>(out + (size_t(b) * 4096 + token) * 128 + h * 16);
+  o[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
+  o[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
+  o[2] = make_float4(acc[8] * inv, acc[9] * inv, acc[10] * inv, acc[11] * inv);
+  o[3] = make_float4(acc[12] * inv, acc[13] * inv, acc[14] * inv, acc[15] * inv);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Second half of output_upscaling fused with the hypernetwork product
+// (SA/modeling/mask_decoder.py:53-59,154-167): for every 128x128 pixel u[64] (after ConvT1+LN2d+GELU)
+//   logit[m][2Y+dy][2X+dx] = sum_c hyper[b][m][c] * GELU(b2[c] + sum_k W2[k][c][dy][dx] u[k])
+// so the (B,32,256,256) upscaled embedding is never written.
+// One thread per (prompt, 128x128 pixel); W2 staged in smem as [dydx][c][k], all threads broadcast-read.
+// ------------------------------------------------------------------------------------------------
+template <int NM>
+__global__ void __launch_bounds__(128)
+upscale2_hyper_kernel(const float* __restrict__ u1 /*[B][4096][4][64]*/, const float* __restrict__ w2r /*[4][32][64]*/,
+                      const float* __restrict__ b2, const float* __restrict__ hyper /*[B][NM][32]*/,
+                      float* __restrict__ low /*[B][NM][256][256]*/, int B) {
+  __shared__ __align__(16) float sw[4 * 32 * 64];
+  __shared__ float sb[32];
+  for (int i = threadIdx.x; i < 4 * 32 * 64; i += blockDim.x) sw[i] = w2r[i];
+  if (threadIdx.x < 32) sb[threadIdx.x] = b2[threadIdx.x];
+  __syncthreads();
+  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= size_t(B) * 16384) return;
+  const int b = int(idx / 16384), rem = int(idx % 16384);
+  const int token = rem >> 2, d1 = rem & 3;
+  const int Y = 2 * (token >> 6) + (d1 >> 1), X = 2 * (token & 63) + (d1 & 1);     // 128x128 position
+  float u[64];
+  const float4* src = reinterpret_cast<const float4*>(u1 + idx * 64);
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const float4 t = src[i];
+    u[4 * i] = t.x; u[4 * i + 1] = t.y; u[4 * i + 2] = t.z; u[4 * i + 3] = t.w;
+  }
+  float hy[NM][32];
+#pragma unroll
+  for (int m = 0; m < NM; ++m)
+#pragma unroll
+    for (int c = 0; c < 32; ++c) hy[m][c] = __ldg(hyper + (size_t(b) * NM + m) * 32 + c);
+#pragma unroll
+  for (int d2 = 0; d2 < 4; ++d2) {
+    float o[NM];
+#pragma unroll
+    for (int m = 0; m < NM; ++m) o[m] = 0.f;
+#pragma unroll 4
+    for (int c = 0; c < 32; ++c) {
+      const float4* wr = reinterpret_cast<const float4*>(sw + (d2 * 32 + c) * 64);
+      float a = sb[c];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const float4 w = wr[k];
+        a = fmaf(u[4 * k], w.x, a); a = fmaf(u[4 * k + 1], w.y, a); a = fmaf(u[4 * k + 2], w.z, a); a = fmaf(u[4 * k + 3], w.w, a);
+      }
+      a = gelu_erf_f(a);
+#pragma unroll
+      for (int m = 0; m < NM; ++m) o[m] = fmaf(hy[m][c], a, o[m]);
+    }
+    const int y = 2 * Y + (d2 >> 1), x = 2 * X + (d2 & 1);
+#pragma unroll
+    for (int m = 0; m < NM; ++m) low[((size_t(b) * NM + m) * 256 + y) * 256 + x] = o[m];
+  }
+}
+
+// gather rows: out[b][j][:] = in[b][t0 + j*tstride][:]   (mask tokens / iou token extraction, slicing)
+__global__ void gather_token_kernel(const float* __restrict__ in, int T, int t0, float* __restrict__ out, int B) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 256) return;
+  out[i] = in[(size_t(i / 256) * T + t0) * 256 + i % 256];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused post-processing (SA/modeling/sam.py:133-162 + SA/predictor.py:242-243 + the driver's painter,
+// Generate Dataset/main_sam_hbox_semantic.py:162,195-199) for tiles whose input and original size are
+// both 1024x1024 (second interpolate is the identity).  ATen's align_corners=False rule
+// (ATen/native/UpSample.h area_pixel_compute_source_index): src = 0.25*(dst+0.5)-0.5 clamped at 0.
+// Arithmetic is spelled with explicit round-to-nearest mul/add (no FMA contraction) in the order
+//   r(y) = l0x*a[y][x0] + l1x*a[y][x1];   v = l0y*r(y0) + l1y*r(y1)
+// so the thresholded result is bit-identical to the oracle's restatement.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void src_index_x4(int d, int in_size, int& i0, int& i1, float& l0, float& l1) {
+  float s = __fsub_rn(__fmul_rn(0.25f, __fadd_rn(float(d), 0.5f)), 0.5f);
+  s = fmaxf(s, 0.f);
+  i0 = int(s);
+  i1 = min(i0 + 1, in_size - 1);
+  l1 = __fsub_rn(s, float(i0));
+  l0 = __fsub_rn(1.0f, l1);
+}
+__device__ __forceinline__ float bilerp(const float* __restrict__ a, int y0, int y1, float ly0, float ly1, int x0, int x1,
+                                        float lx0, float lx1) {
+  const float r0 = __fadd_rn(__fmul_rn(lx0, a[y0 * 256 + x0]), __fmul_rn(lx1, a[y0 * 256 + x1]));
+  const float r1 = __fadd_rn(__fmul_rn(lx0, a[y1 * 256 + x0]), __fmul_rn(lx1, a[y1 * 256 + x1]));
+  return __fadd_rn(__fmul_rn(ly0, r0), __fmul_rn(ly1, r1));
+}
+
+// masks (u8 0/1 == torch.bool) and/or full-resolution logits for NB low-res maps
+__global__ void upsample4_threshold_kernel(const float* __restrict__ low /*[NB][256][256]*/, uint8_t* __restrict__ masks /*[NB][1024][1024] or null*/,
+                                           float* __restrict__ logits /*or null*/, int NB) {
+  const int x4 = blockIdx.x * blockDim.x + threadIdx.x;     // group of 4 output pixels
+  const int y = blockIdx.y, b = blockIdx.z;
+  if (x4 >= 256) return;
+  const float* a = low + size_t(b) * 65536;
+  int y0, y1;
+  float ly0, ly1;
+  src_index_x4(y, 256, y0, y1, ly0, ly1);
+  uint32_t pk = 0;
+  float v[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int x0, x1;
+    float lx0, lx1;
+    src_index_x4(x4 * 4 + i, 256, x0, x1, lx0, lx1);
+    v[i] = bilerp(a, y0, y1, ly0, ly1, x0, x1, lx0, lx1);
+    pk |= (v[i] > 0.0f ? 1u : 0u) << (8 * i);
+  }
+  const size_t o = (size_t(b) * 1024 + y) * 1024 + x4 * 4;
+  if (masks) *reinterpret_cast<uint32_t*>(masks + o) = pk;
+  if (logits) *reinterpret_cast<float4*>(logits + o) = make_float4(v[0], v[1], v[2], v[3]);
+}
+
+// semantic label map: label of the highest-index prompt whose mask is true, else the existing canvas value
+__global__ void upsample4_paint_kernel(const float* __restrict__ low /*[NB][256][256]*/, const int* __restrict__ labels, int NB,
+                                       uint8_t* __restrict__ canvas /*[1024][1024]*/) {
+  const int x4 = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  if (x4 >= 256) return;
+  int y0, y1;
+  float ly0, ly1;
+  src_index_x4(y, 256, y0, y1, ly0, ly1);
+  int x0[4], x1[4];
+  float lx0[4], lx1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) src_index_x4(x4 * 4 + i, 256, x0[i], x1[i], lx0[i], lx1[i]);
+  uint32_t cur = *reinterpret_cast<uint32_t*>(canvas + size_t(y) * 1024 + x4 * 4);
+  uint32_t undecided = 0xF;
+  for (int b = NB - 1; b >= 0 && undecided; --b) {
+    const float* a = low + size_t(b) * 65536;
+    const uint32_t lab = uint32_t(labels[b]) & 0xFF;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if ((undecided >> i) & 1) {
+        if (bilerp(a, y0, y1, ly0, ly1, x0[i], x1[i], lx0[i], lx1[i]) > 0.0f) {
+          cur = (cur & ~(0xFFu << (8 * i))) | (lab << (8 * i));
+          undecided &= ~(1u << i);
+        }
+      }
+    }
+  }
+  *reinterpret_cast<uint32_t*>(canvas + size_t(y) * 1024 + x4 * 4) = cur;
+}
+
+// general bilinear resize (align_corners=False, ATen scale = in/out) of a cropped source view
+__global__ void bilinear_resize_kernel(const float* __restrict__ in, int in_ld, int in_plane, int in_h, int in_w,
+                                       float* __restrict__ out_f, uint8_t* __restrict__ out_mask, int out_h, int out_w, int NB) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, b = blockIdx.z;
+  if (x >= out_w) return;
+  const float sy = float(in_h) / float(out_h), sx = float(in_w) / float(out_w);
+  float fy = fmaxf(__fsub_rn(__fmul_rn(sy, __fadd_rn(float(y), 0.5f)), 0.5f), 0.f);
+  float fx = fmaxf(__fsub_rn(__fmul_rn(sx, __fadd_rn(float(x), 0.5f)), 0.5f), 0.f);
+  const int y0 = int(fy), x0 = int(fx);
+  const int y1 = y0 + (y0 < in_h - 1 ? 1 : 0), x1 = x0 + (x0 < in_w - 1 ? 1 : 0);
+  const float ly1 = __fsub_rn(fy, float(y0)), lx1 = __fsub_rn(fx, float(x0));
+  const float ly0 = __fsub_rn(1.0f, ly1), lx0 = __fsub_rn(1.0f, lx1);
+  const float* a = in + size_t(b) * in_plane;
+  const float r0 = __fadd_rn(__fmul_rn(lx0, a[y0 * in_ld + x0]), __fmul_rn(lx1, a[y0 * in_ld + x1]));
+  const float r1 = __fadd_rn(__fmul_rn(lx0, a[y1 * in_ld + x0]), __fmul_rn(lx1, a[y1 * in_ld + x1]));
+  const float v = __fadd_rn(__fmul_rn(ly0, r0), __fmul_rn(ly1, r1));
+  const size_t o = (size_t(b) * out_h + y) * out_w + x;
+  if (out_f) out_f[o] = v;
+  if (out_mask) out_mask[o] = v > 0.0f ? 1 : 0;
+}
+
+}  // namespace samrs

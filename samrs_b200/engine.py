@@ -1,0 +1,217 @@
+"""ctypes binding of `libsamrs_b200.so` (C ABI in include/samrs_b200.h).
+
+PyTorch is used here only for device memory, streams and dtype plumbing: every
+tensor handed to the library is passed as a raw `data_ptr()` plus sizes.  There
+is no CPU path: if the library is missing, or no sm_100 GPU is present,
+constructing an `Engine` raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from .config import SamGeometry, geometry
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsamrs_b200.so")
+_lib: Optional[ctypes.CDLL] = None
+
+# name -> (restype, argtypes); must list every symbol declared in include/samrs_b200.h
+_vp, _i, _i64p = ctypes.c_void_p, ctypes.c_int, ctypes.POINTER(ctypes.c_int64)
+ABI = {
+    "samrs_create": (_i, [_i, _i, _i, _i, ctypes.POINTER(_i), _i, ctypes.POINTER(_vp)]),
+    "samrs_load_weights": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_char_p), ctypes.POINTER(_vp), _i64p, _vp]),
+    "samrs_encode": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp]),
+    "samrs_set_features": (_i, [_vp, _vp, _vp]),
+    "samrs_decode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
+    "samrs_postprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "samrs_semantic_reduce": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    "samrs_launch_count": (_i, [_vp, _i64p]),
+    "samrs_last_error": (ctypes.c_char_p, [_vp]),
+    "samrs_destroy": (None, [_vp]),
+    "samrs_test_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
+    "samrs_test_attention": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
+    "samrs_test_sgemm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+}
+
+
+def load_library() -> ctypes.CDLL:
+    """dlopen the in-tree library and bind every ABI symbol; raises if it was not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            raise RuntimeError(
+                f"{_LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(samrs_b200 has no CPU or PyTorch fallback)")
+        lib = ctypes.CDLL(_LIB_PATH)
+        for name, (res, args) in ABI.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+class Engine:
+    """One engine per (GPU, stream).  All methods enqueue on torch's current stream of `device`."""
+
+    def __init__(self, variant_or_geometry, device="cuda"):
+        g = variant_or_geometry if isinstance(variant_or_geometry, SamGeometry) else geometry(variant_or_geometry)
+        self.geometry = g
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("samrs_b200 runs on CUDA devices only (no CPU path)")
+        if self.device.index is None:
+            self.device = torch.device("cuda", torch.cuda.current_device())
+        self._lib = load_library()
+        self._h = ctypes.c_void_p()
+        gi = (ctypes.c_int * len(g.global_attn_indexes))(*g.global_attn_indexes)
+        rc = self._lib.samrs_create(self.device.index, g.embed_dim, g.depth, g.num_heads, gi,
+                                    len(g.global_attn_indexes), ctypes.byref(self._h))
+        if rc != 0:
+            raise RuntimeError("samrs_create failed: " + self._lib.samrs_last_error(None).decode())
+        self.weights_loaded = False
+
+    # -- helpers -----------------------------------------------------------------
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: {self._lib.samrs_last_error(self._h).decode()}")
+
+    def _dev(self, t: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+        if t.device != self.device:
+            raise ValueError(f"tensor on {t.device}, engine on {self.device}")
+        return t.to(dtype).contiguous()
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) and self._h.value:
+            self._lib.samrs_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- API ---------------------------------------------------------------------
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor]) -> None:
+        """Strict load of a reference-layout `Sam.state_dict()` (any device; staged to the GPU as fp32)."""
+        from .weights import check_state_dict
+        check_state_dict(self.geometry, state_dict)
+        names = list(state_dict.keys())
+        staged = [state_dict[k].detach().to(device=self.device, dtype=torch.float32).contiguous() for k in names]
+        n = len(names)
+        c_names = (ctypes.c_char_p * n)(*[k.encode() for k in names])
+        c_ptrs = (ctypes.c_void_p * n)(*[t.data_ptr() for t in staged])
+        c_numel = (ctypes.c_int64 * n)(*[t.numel() for t in staged])
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_load_weights(self._h, n, c_names, c_ptrs, c_numel, _stream(self.device)), "load_weights")
+            torch.cuda.current_stream(self.device).synchronize()   # staged tensors are freed on return
+        self.weights_loaded = True
+
+    def encode(self, image_u8: torch.Tensor, chw: bool = False) -> torch.Tensor:
+        """uint8 image on the device, HWC (or CHW) with H,W <= 1024 -> features (1,256,64,64) fp32."""
+        img = self._dev(image_u8, torch.uint8)
+        H, W = (img.shape[1], img.shape[2]) if chw else (img.shape[0], img.shape[1])
+        feats = torch.empty((1, 256, 64, 64), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_encode(self._h, img.data_ptr(), H, W, int(chw), feats.data_ptr(), _stream(self.device)), "encode")
+        return feats
+
+    def set_features(self, features: torch.Tensor) -> None:
+        f = self._dev(features, torch.float32)
+        assert tuple(f.shape) == (1, 256, 64, 64)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_set_features(self._h, f.data_ptr(), _stream(self.device)), "set_features")
+
+    def decode(self, boxes: Optional[torch.Tensor] = None, point_coords: Optional[torch.Tensor] = None,
+               point_labels: Optional[torch.Tensor] = None, mask_input: Optional[torch.Tensor] = None,
+               multimask_output: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+        """-> (low_res (B,C,256,256) fp32, iou (B,C) fp32)."""
+        b = self._dev(boxes, torch.float32) if boxes is not None else None
+        pc = self._dev(point_coords, torch.float32) if point_coords is not None else None
+        pl = self._dev(point_labels, torch.int32) if point_labels is not None else None
+        mi = self._dev(mask_input, torch.float32) if mask_input is not None else None
+        if pc is not None:
+            B, NP = pc.shape[0], pc.shape[1]
+        elif b is not None:
+            B, NP = b.shape[0], 0
+        elif mi is not None:
+            B, NP = mi.shape[0], 0
+        else:
+            raise ValueError("decode needs at least one prompt kind")
+        C = 3 if multimask_output else 1
+        low = torch.empty((B, C, 256, 256), dtype=torch.float32, device=self.device)
+        iou = torch.empty((B, C), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_decode(self._h, _ptr(b), _ptr(pc), _ptr(pl), NP, _ptr(mi), B, int(multimask_output),
+                                               low.data_ptr(), iou.data_ptr(), _stream(self.device)), "decode")
+        return low, iou
+
+    def postprocess(self, low_res: torch.Tensor, input_size: Sequence[int], original_size: Sequence[int],
+                    return_logits: bool = False) -> torch.Tensor:
+        """(B,C,256,256) -> (B,C,H,W) bool masks (or fp32 logits)."""
+        low = self._dev(low_res, torch.float32)
+        B, C = low.shape[0], low.shape[1]
+        oh, ow = int(original_size[0]), int(original_size[1])
+        if return_logits:
+            out = torch.empty((B, C, oh, ow), dtype=torch.float32, device=self.device)
+            args = (None, out.data_ptr())
+        else:
+            out = torch.empty((B, C, oh, ow), dtype=torch.bool, device=self.device)
+            args = (out.data_ptr(), None)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_postprocess(self._h, low.data_ptr(), B * C, int(input_size[0]), int(input_size[1]), oh, ow,
+                                                    args[0], args[1], _stream(self.device)), "postprocess")
+        return out
+
+    def semantic_reduce(self, low_res: torch.Tensor, class_ids: torch.Tensor, label_map: torch.Tensor) -> torch.Tensor:
+        """In-place painter reduce of (B,[1,]256,256) logits into a (1024,1024) uint8 label map (255-initialised by the caller)."""
+        low = self._dev(low_res, torch.float32)
+        ids = self._dev(class_ids, torch.int32)
+        assert label_map.dtype == torch.uint8 and label_map.is_contiguous() and label_map.device == self.device
+        B = low.shape[0]
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_semantic_reduce(self._h, low.data_ptr(), ids.data_ptr(), B, label_map.data_ptr(),
+                                                        label_map.shape[0], label_map.shape[1], _stream(self.device)), "semantic_reduce")
+        return label_map
+
+    def launch_count(self) -> int:
+        c = ctypes.c_int64(0)
+        self._lib.samrs_launch_count(self._h, ctypes.byref(c))
+        return int(c.value)
+
+    # -- kernel-level test hooks ---------------------------------------------------
+    def test_gemm(self, A: torch.Tensor, B: torch.Tensor, out_half: bool, bias=None, res=None, gelu=False, force_bn=0):
+        M, K = A.shape
+        N = B.shape[0]
+        out = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_test_gemm(self._h, A.data_ptr(), B.data_ptr(), M, N, K, out.data_ptr(), int(out_half),
+                                                  _ptr(bias), _ptr(res), int(gelu), force_bn, _stream(self.device)), "test_gemm")
+        return out
+
+    def test_attention(self, qkv: torch.Tensor, rel_pos_h: torch.Tensor, rel_pos_w: torch.Tensor, global_block: bool):
+        out = torch.empty((4096, self.geometry.embed_dim), dtype=torch.float16, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_test_attention(self._h, qkv.data_ptr(), rel_pos_h.data_ptr(), rel_pos_w.data_ptr(),
+                                                       int(global_block), out.data_ptr(), _stream(self.device)), "test_attention")
+        return out
+
+    def test_sgemm(self, A: torch.Tensor, W: torch.Tensor, bias=None, act=0):
+        M, K = A.shape
+        N = W.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_test_sgemm(self._h, A.data_ptr(), W.data_ptr(), out.data_ptr(), _ptr(bias), M, N, K, act,
+                                                   _stream(self.device)), "test_sgemm")
+        return out

@@ -161,9 +161,9 @@ def synthetic_state_dict(variant: str, seed: int = 0) -> Dict[str, torch.Tensor]
     return {k: _draw(k, shp, kind, seed) for k, shp, kind in state_dict_spec(g)}
 
 
-def check_state_dict(variant: str, sd: Dict[str, torch.Tensor]) -> None:
+def check_state_dict(variant, sd: Dict[str, torch.Tensor]) -> None:
     """Strict key/shape check, same contract as `load_state_dict(strict=True)`."""
-    spec = state_dict_spec(geometry(variant))
+    spec = state_dict_spec(variant if isinstance(variant, SamGeometry) else geometry(variant))
     want = {k: shp for k, shp, _ in spec}
     missing = [k for k in want if k not in sd]
     unexpected = [k for k in sd if k not in want]

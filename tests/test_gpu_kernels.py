@@ -1,0 +1,121 @@
+"""Kernel-level parity on a B200: tcgen05 GEMM / attention and the decoder SGEMM against plain torch fp32
+references of the same op (floating-point kernels; tolerances stated per test)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng64():
+    from samrs_b200.engine import Engine
+    return Engine("vit_t64", "cuda:0")
+
+
+@pytest.fixture(scope="module")
+def eng80():
+    from samrs_b200.engine import Engine
+    return Engine("vit_t80", "cuda:0")
+
+
+def _rand(shape, seed, scale=1.0, dtype=torch.float16):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [
+    (128, 128, 64, 128), (128, 256, 128, 256), (256, 160, 192, 160),
+    (4096, 3840, 1280, 0), (4096, 1280, 5120, 0), (4096, 5120, 1280, 0),
+    (4096, 384, 128, 0), (200, 136, 160, 0), (4096, 480, 160, 0), (4096, 256, 2304, 0),
+])
+def test_gemm_fp32_out_bias_residual(eng64, M, N, K, bn):
+    A, B = _rand((M, K), 1), _rand((N, K), 2, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 3, dtype=torch.float32)
+    res = _rand((M, N), 4, dtype=torch.float32)
+    ref = A.float() @ B.float().t() + bias + res
+    out = eng64.test_gemm(A, B, out_half=False, bias=bias, res=res, force_bn=bn)
+    torch.cuda.synchronize()
+    # fp16 products are exact in fp32; only the accumulation order differs
+    err = (out - ref).abs().max().item()
+    assert err < 2e-3, f"max err {err}"
+
+
+@pytest.mark.parametrize("M,N,K,gelu", [(4096, 3840, 1280, False), (4096, 5120, 1280, True), (384, 520, 136, True)])
+def test_gemm_fp16_out(eng64, M, N, K, gelu):
+    A, B = _rand((M, K), 5), _rand((N, K), 6, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 7, dtype=torch.float32)
+    ref = A.float() @ B.float().t() + bias
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    out = eng64.test_gemm(A, B, out_half=True, bias=bias, gelu=gelu)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    assert err < 6e-3, f"max err {err}"       # fp16 output rounding of |values| <~ 6
+
+
+def _attention_reference(qkv, rph, rpw, heads, hd, global_block):
+    """image_encoder.py:224-240 + :325-361 on fp32 copies of the fp16 activation; padded tokens have q=k=v=0
+    (the engine drops the K/V biases, see attn_tc.cuh)."""
+    D = heads * hd
+    x = qkv.float().view(64, 64, 3, heads, hd)
+    if global_block:
+        S, xs = 64, x.unsqueeze(0)
+    else:
+        S = 14
+        xp = torch.zeros(70, 70, 3, heads, hd, device=x.device)
+        xp[:64, :64] = x
+        xs = xp.view(5, 14, 5, 14, 3, heads, hd).permute(0, 2, 1, 3, 4, 5, 6).reshape(25, 14, 14, 3, heads, hd)
+    nb = xs.shape[0]
+    q, k, v = [xs[:, :, :, i].permute(0, 3, 1, 2, 4).reshape(nb * heads, S * S, hd) for i in range(3)]
+    idx = torch.arange(S, device=x.device)[:, None] - torch.arange(S, device=x.device)[None, :] + (S - 1)
+    Rh, Rw = rph[idx], rpw[idx]
+    out = torch.empty(nb * heads, S * S, hd, device=x.device)
+    for i0 in range(0, nb * heads, 8):
+        qq, kk, vv = q[i0:i0 + 8], k[i0:i0 + 8], v[i0:i0 + 8]
+        a = (qq * hd ** -0.5) @ kk.transpose(-2, -1)
+        rq = qq.reshape(-1, S, S, hd)
+        rel_h = torch.einsum("bhwc,hkc->bhwk", rq, Rh)
+        rel_w = torch.einsum("bhwc,wkc->bhwk", rq, Rw)
+        a = (a.view(-1, S, S, S, S) + rel_h[..., :, None] + rel_w[..., None, :]).view(-1, S * S, S * S)
+        out[i0:i0 + 8] = a.softmax(-1) @ vv
+    o = out.view(nb, heads, S, S, hd).permute(0, 2, 3, 1, 4).reshape(nb, S, S, D)
+    if not global_block:
+        o = o.view(5, 5, 14, 14, D).permute(0, 2, 1, 3, 4).reshape(70, 70, D)[:64, :64]
+    return o.reshape(4096, D)
+
+
+@pytest.mark.parametrize("which,global_block", [("eng64", False), ("eng64", True), ("eng80", False), ("eng80", True)])
+def test_encoder_attention(request, which, global_block):
+    eng = request.getfixturevalue(which)
+    g = eng.geometry
+    heads, hd, D = g.num_heads, g.head_dim, g.embed_dim
+    S = 64 if global_block else 14
+    qkv = _rand((4096, 3 * D), 11, 1.0)
+    rph = _rand((2 * S - 1, hd), 12, 0.1, torch.float32)
+    rpw = _rand((2 * S - 1, hd), 13, 0.1, torch.float32)
+    ref = _attention_reference(qkv, rph, rpw, heads, hd, global_block)
+    out = eng.test_attention(qkv, rph, rpw, global_block)
+    torch.cuda.synchronize()
+    err = (out.float() - ref).abs().max().item()
+    # fp16 P (<= 2^-11 relative) and fp16 output rounding on |o| <~ 1
+    assert err < 4e-3, f"max err {err} (ref absmax {ref.abs().max().item()})"
+
+
+@pytest.mark.parametrize("M,N,K,act", [(224, 256, 256, 0), (4096 * 3, 128, 256, 0), (77, 2048, 256, 1), (77, 256, 2048, 0), (1, 32, 256, 0), (500, 256, 128, 2)])
+def test_decoder_sgemm(eng64, M, N, K, act):
+    A, W = _rand((M, K), 21, dtype=torch.float32), _rand((N, K), 22, 1.0 / math.sqrt(K), torch.float32)
+    bias = _rand((N,), 23, dtype=torch.float32)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    ref = A @ W.t() + bias
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    if act == 1:
+        ref = torch.relu(ref)
+    elif act == 2:
+        ref = torch.nn.functional.gelu(ref)
+    out = eng64.test_sgemm(A, W, bias, act)
+    torch.cuda.synchronize()
+    err = (out - ref).abs().max().item()
+    assert err < 1e-4, f"max err {err}"
