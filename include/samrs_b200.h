@@ -60,6 +60,12 @@ int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int i
 int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_ids, int B,
                           uint8_t* label_map_inout, int H, int W, void* stream);
 
+/* device-side timing by kernel category (bench.py's roofline): enable=1 starts recording CUDA events around the
+ * engine's launches on their stream; enable=0 synchronises and returns milliseconds / scope counts per category:
+ * 0 tcgen05 GEMM, 1 windowed attention, 2 global attention, 3 rel-pos terms, 4 LayerNorm, 5 whole encode,
+ * 6 decode call, 7 post-processing / painter. */
+int samrs_profile(void* engine, int enable, float* ms_by_category, int* launches_by_category, int ncat);
+
 /* kernels launched by this engine since creation (bench.py's gpu_launches). */
 int samrs_launch_count(void* engine, int64_t* count_out);
 

@@ -133,6 +133,27 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   SAMRS_FAIL("gemm: unsupported N tile");
 }
 
+// ------------------------------------------------------------------ per-category device timing (bench.py roofline)
+enum ProfCat { PC_GEMM = 0, PC_ATTN_WIN, PC_ATTN_GLOB, PC_RELPOS, PC_LN, PC_ENC_OTHER, PC_DECODER, PC_EPILOGUE, PC_COUNT };
+struct ProfRec { int cat; cudaEvent_t a, b; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+static Profiler* g_prof = nullptr;
+struct ProfScope {
+  cudaStream_t st; ProfRec r; bool active;
+  ProfScope(int cat, cudaStream_t s) : st(s), active(g_prof && g_prof->on) {
+    if (active) { r.cat = cat; r.a = g_prof->get(); r.b = g_prof->get(); cudaEventRecord(r.a, st); }
+  }
+  ~ProfScope() { if (active) { cudaEventRecord(r.b, st); g_prof->recs.push_back(r); } }
+};
+
 // ------------------------------------------------------------------ engine state
 struct BlockWeights {
   float *ln1w, *ln1b, *ln2w, *ln2b;
@@ -159,6 +180,7 @@ struct Engine {
   std::vector<int> global_idx;
   int num_sms = 148;
   int64_t launches = 0;
+  Profiler prof;
   std::string err;
   std::vector<void*> allocs;
   bool weights_loaded = false, image_set = false;
@@ -271,9 +293,13 @@ static int launch_attn_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, const
 static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, const float* rph, const float* rpw, bool global,
                              __half* out) {
   const int D = e->D, hd = e->hd, S = global ? 64 : 14;
-  if (hd == 64) SAMRS_TRY(launch_relpos<64>(st, qkv, 3 * D, rph, rpw, S, e->heads, e->rel));
-  else if (hd == 80) SAMRS_TRY(launch_relpos<80>(st, qkv, 3 * D, rph, rpw, S, e->heads, e->rel));
-  else SAMRS_FAIL("head_dim must be 64 or 80");
+  {
+    ProfScope ps(PC_RELPOS, st);
+    if (hd == 64) SAMRS_TRY(launch_relpos<64>(st, qkv, 3 * D, rph, rpw, S, e->heads, e->rel));
+    else if (hd == 80) SAMRS_TRY(launch_relpos<80>(st, qkv, 3 * D, rph, rpw, S, e->heads, e->rel));
+    else SAMRS_FAIL("head_dim must be 64 or 80");
+  }
+  ProfScope ps2(global ? PC_ATTN_GLOB : PC_ATTN_WIN, st);
   AttnParams p;
   p.rel = e->rel;
   p.out = out;
@@ -547,6 +573,7 @@ static int gemm_enc(Engine* e, cudaStream_t st, const __half* A, int lda, const 
   p.out = out; p.ldc = ldc;
   p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.tiles_m = p.tiles_n = 0;
+  ProfScope ps(PC_GEMM, st);
   return launch_gemm_tc(A, lda, W, K, p, out_half, act, e->num_sms, st, 0);
 }
 
@@ -574,11 +601,11 @@ static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, flo
   SAMRS_TRY(gemm_enc(e, st, e->a_pe, 768, e->w_patch, T, D, 768, e->x, D, false, e->b_patch, e->pos_embed, D, 0, 0));
   for (int i = 0; i < e->depth; ++i) {
     const BlockWeights& b = e->blocks[i];
-    SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln1w, b.ln1b, 1e-6f, e->xn, D, T, D)));
+    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln1w, b.ln1b, 1e-6f, e->xn, D, T, D))); }
     SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.wqkv, T, 3 * D, D, e->qkv, 3 * D, true, b.bqkv_eff, nullptr, 0, 0, 0));
     SAMRS_TRY(encoder_attention(e, st, e->qkv, b.rph, b.rpw, b.global, e->attn_o));
     SAMRS_TRY(gemm_enc(e, st, e->attn_o, D, b.wproj, T, D, D, e->x, D, false, b.bproj_eff, e->x, D, 0, 0));
-    SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln2w, b.ln2b, 1e-6f, e->xn, D, T, D)));
+    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln2w, b.ln2b, 1e-6f, e->xn, D, T, D))); }
     SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.w1, T, 4 * D, D, e->hid, 4 * D, true, b.b1, nullptr, 0, 0, 1));
     SAMRS_TRY(gemm_enc(e, st, e->hid, 4 * D, b.w2, T, D, 4 * D, e->x, D, false, b.b2, e->x, D, 0, 0));
   }
@@ -764,8 +791,8 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
 using namespace samrs;
 
 struct LaunchScope {
-  explicit LaunchScope(Engine* e) { g_launch_counter = e ? &e->launches : nullptr; }
-  ~LaunchScope() { g_launch_counter = nullptr; }
+  explicit LaunchScope(Engine* e) { g_launch_counter = e ? &e->launches : nullptr; g_prof = e ? &e->prof : nullptr; }
+  ~LaunchScope() { g_launch_counter = nullptr; g_prof = nullptr; }
 };
 
 extern "C" {
@@ -814,6 +841,7 @@ int samrs_encode(void* engine, const uint8_t* img, int H, int W, int chw, float*
   if (!e) return 1;
   cudaSetDevice(e->device);
   LaunchScope ls(e);
+  ProfScope ps(PC_ENC_OTHER, static_cast<cudaStream_t>(stream));   // whole encode; "other" = this minus the categories
   return set_err(e, encode_impl(e, img, H, W, chw, features_out, static_cast<cudaStream_t>(stream)));
 }
 
@@ -840,6 +868,7 @@ int samrs_decode(void* engine, const float* boxes, const float* points, const in
   if (points && !labels) return set_err(e, samrs::fail(__FILE__, __LINE__, "decode: point labels missing"));
   const int C = multimask ? 3 : 1;
   const int CH = 64;     // prompts per pass (bounds scratch at ~1.3 GB)
+  ProfScope ps(PC_DECODER, static_cast<cudaStream_t>(stream));
   for (int b0 = 0; b0 < B; b0 += CH) {
     const int nb = (B - b0 < CH) ? (B - b0) : CH;
     int rc = decode_chunk(e, static_cast<cudaStream_t>(stream), boxes ? boxes + size_t(b0) * 4 : nullptr,
@@ -859,6 +888,7 @@ int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int i
   LaunchScope ls(e);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (NB < 1) return 0;
+  ProfScope ps(PC_EPILOGUE, st);
   if (in_h == 1024 && in_w == 1024 && out_h == 1024 && out_w == 1024) {
     for (int b0 = 0; b0 < NB; b0 += 32768) {
       const int nb = NB - b0 < 32768 ? NB - b0 : 32768;
@@ -892,9 +922,33 @@ int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_id
   LaunchScope ls(e);
   if (H != 1024 || W != 1024) return set_err(e, samrs::fail(__FILE__, __LINE__, "semantic_reduce: only 1024x1024 tiles are supported"));
   if (B < 1) return 0;
+  ProfScope ps(PC_EPILOGUE, static_cast<cudaStream_t>(stream));
   upsample4_paint_kernel<<<dim3(1, 1024), 256, 0, static_cast<cudaStream_t>(stream)>>>(lowres, class_ids, B, label_map);
   count_launch();
   if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "semantic_reduce launch failed"));
+  return 0;
+}
+
+int samrs_profile(void* engine, int enable, float* ms_by_category, int* launches_by_category, int ncat) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  if (enable) {
+    for (auto& r : e->prof.recs) { e->prof.pool.push_back(r.a); e->prof.pool.push_back(r.b); }
+    e->prof.recs.clear();
+    e->prof.on = true;
+    return 0;
+  }
+  e->prof.on = false;
+  if (cudaDeviceSynchronize() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "profile: device sync failed"));
+  for (int i = 0; i < ncat; ++i) { if (ms_by_category) ms_by_category[i] = 0.f; if (launches_by_category) launches_by_category[i] = 0; }
+  for (auto& r : e->prof.recs) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.cat < ncat) { if (ms_by_category) ms_by_category[r.cat] += ms; if (launches_by_category) launches_by_category[r.cat] += 1; }
+    e->prof.pool.push_back(r.a); e->prof.pool.push_back(r.b);
+  }
+  e->prof.recs.clear();
   return 0;
 }
 

@@ -28,6 +28,7 @@ ABI = {
     "samrs_decode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "samrs_postprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "samrs_semantic_reduce": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    "samrs_profile": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _i]),
     "samrs_launch_count": (_i, [_vp, _i64p]),
     "samrs_last_error": (ctypes.c_char_p, [_vp]),
     "samrs_destroy": (None, [_vp]),
@@ -184,6 +185,18 @@ class Engine:
             self._check(self._lib.samrs_semantic_reduce(self._h, low.data_ptr(), ids.data_ptr(), B, label_map.data_ptr(),
                                                         label_map.shape[0], label_map.shape[1], _stream(self.device)), "semantic_reduce")
         return label_map
+
+    PROFILE_CATEGORIES = ("gemm_tc", "attn_window", "attn_global", "relpos", "layernorm", "encode_total", "decode_total", "epilogue")
+
+    def profile_begin(self) -> None:
+        self._check(self._lib.samrs_profile(self._h, 1, None, None, 0), "profile")
+
+    def profile_end(self):
+        """-> {category: (milliseconds, scopes)} accumulated since profile_begin (synchronises the device)."""
+        n = len(self.PROFILE_CATEGORIES)
+        ms, cnt = (ctypes.c_float * n)(), (ctypes.c_int * n)()
+        self._check(self._lib.samrs_profile(self._h, 0, ms, cnt, n), "profile")
+        return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_CATEGORIES)}
 
     def launch_count(self) -> int:
         c = ctypes.c_int64(0)
