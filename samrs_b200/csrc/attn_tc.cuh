@@ -24,7 +24,8 @@
 namespace samrs {
 
 struct AttnParams {
-  const float* rel;     // [heads][4096][2*BX] fp32, pre-multiplied by log2(e): rel_h[kh] then rel_w[kw]
+  const float* rel;     // [heads][4096][NP] fp32 (NP = 256 global / 64 windowed), log2(e) * q.[rel_pos_h ; rel_pos_w]:
+                        //   rel_h[kh] = rel[qh - kh + S-1],  rel_w[kw] = rel[(2S-1) + qw - kw + S-1]
   __half* out;          // [4096][D] fp16, head-major columns (h*HD + c)
   int D;                // embed dim
   int heads;
@@ -213,10 +214,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
       const int ty = qy0 + r / BX, tx = x0 + r % BX;
       const bool valid = (r < QR) && ty < 64 && tx < 64;
       const int token = ty * 64 + tx;
-      const float* relrow = p.rel + (size_t(head) * 4096 + (valid ? token : 0)) * (2 * BX);
+      constexpr int NP = (BX == 64) ? 256 : 64;
+      constexpr int SS = BX;                                  // 64 (global) or 14 (window): rel-pos table half-size
+      const float* relrow = p.rel + (size_t(head) * 4096 + (valid ? token : 0)) * NP;
+      const int qh = qy0 - ky0 + r / BX, qw = r % BX;
       float relw[BX];
 #pragma unroll
-      for (int i = 0; i < BX; ++i) relw[i] = valid ? __ldg(relrow + BX + i) : 0.f;
+      for (int i = 0; i < BX; ++i) relw[i] = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - i) : 0.f;
       float o_acc[HD];
 #pragma unroll
       for (int i = 0; i < HD; ++i) o_acc[i] = 0.f;
@@ -226,7 +230,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         const int buf = j & 1;
         float relh[KBY];
 #pragma unroll
-        for (int i = 0; i < KBY; ++i) relh[i] = valid ? __ldg(relrow + (NKT == 1 ? 0 : j * KBY) + i) : 0.f;
+        for (int i = 0; i < KBY; ++i) relh[i] = valid ? __ldg(relrow + qh + (SS - 1) - ((NKT == 1 ? 0 : j * KBY) + i)) : 0.f;
         mbar_wait(&s_full[buf], sph[buf]);
         sph[buf] ^= 1;
         tc_fence_after();

@@ -96,8 +96,10 @@ static int launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const 
 }
 
 int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const GemmParams& pin, bool out_half, int act,
-                   int num_sms, cudaStream_t stream, int force_bn) {
+                   int num_sms, cudaStream_t stream, int force_bn, const CUtensorMap* a_map_rank3) {
   GemmParams p = pin;
+  if (p.batch < 1) p.batch = 1;
+  p.a_rank3 = a_map_rank3 ? 1 : 0;
   if (p.K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) SAMRS_FAIL("gemm: K and leading dimensions must be multiples of 8");
   int bn = force_bn;
   if (bn == 0) {
@@ -107,17 +109,18 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
     for (int i = 0; i < 3; ++i) {
       const int c = cands[i];
       const long tm = (p.M + GEMM_BM - 1) / GEMM_BM, tn = (p.N + c - 1) / c;
-      const long waves = (tm * tn + num_sms - 1) / num_sms;
-      const double eff = double(p.M) * p.N / (double(waves) * num_sms * GEMM_BM * c);
+      const long waves = (tm * tn * p.batch + num_sms - 1) / num_sms;
+      const double eff = double(p.M) * p.N * p.batch / (double(waves) * num_sms * GEMM_BM * c);
       if (eff > best + 1e-9) { best = eff; bn = c; }
     }
   }
   p.tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   p.tiles_n = (p.N + bn - 1) / bn;
   CUtensorMap tA, tB;
-  SAMRS_TRY(make_tmap_2d(&tA, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, GEMM_BK, GEMM_BM));
+  if (a_map_rank3) tA = *a_map_rank3;
+  else SAMRS_TRY(make_tmap_2d(&tA, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, GEMM_BK, GEMM_BM));
   SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t(bn)));
-  const int tiles = p.tiles_m * p.tiles_n;
+  const int tiles = p.tiles_m * p.tiles_n * p.batch;
   const int grid = tiles < num_sms ? tiles : num_sms;
 #define SAMRS_GEMM_CASE(BN_)                                                                        \
   if (bn == BN_) {                                                                                  \
@@ -159,7 +162,7 @@ struct BlockWeights {
   float *ln1w, *ln1b, *ln2w, *ln2b;
   __half *wqkv, *wproj, *w1, *w2;
   float *bqkv_eff, *bproj_eff, *b1, *b2;
-  float *rph, *rpw;
+  __half* reltab;       // [256 or 64][hd] fp16: log2(e) * [rel_pos_h ; rel_pos_w ; 0]
   bool global;
 };
 
@@ -199,6 +202,9 @@ struct Engine {
   float *nfw, *nfb, *iou_token, *mask_tokens;
   float *up_w1r, *up_b1r, *up_lnw, *up_lnb, *up_w2r, *up_b2;
   Mlp3 hyper[4], iou_head;
+  // split-fp16 ([hi|hi|lo] x 256) weights of the four tensor-core decoder GEMMs and their epilogue operands
+  __half *wd_p1 = nullptr, *wd_p2 = nullptr, *wd_o0 = nullptr, *wd_o1 = nullptr;
+  float *bias_p1 = nullptr, *bias_p2 = nullptr, *R1 = nullptr, *R2 = nullptr;
   float* dense_pe = nullptr;           // [4096][256]
   float* pek[5] = {nullptr};           // dense_pe * W^T for: l0.t2i.k, l0.i2t.q, l1.t2i.k, l1.i2t.q, final.k  [4096][128]
 
@@ -211,7 +217,10 @@ struct Engine {
   // decoder scratch (sized for dec_cap prompts)
   int dec_cap = 0;
   float *d_tok0, *d_q, *d_tmp256a, *d_tmp256b, *d_tmp256c, *d_tmp256d, *d_tmp128a, *d_tmp128b, *d_tmp128c, *d_mlp;
-  float *d_keys, *d_io, *d_Kp, *d_Vp, *d_Qp, *d_u1, *d_src, *d_hyper, *d_hy_t, *d_hy_a, *d_hy_b, *d_iou_all, *d_low;
+  float *d_keys, *d_P, *d_hyper, *d_hy_t, *d_hy_a, *d_hy_b, *d_iou_all, *d_low;
+  __half *d_keysA, *d_ioA;
+  int mask_cap = 0;                    // mask-prompt path scratch (per-prompt layer-0 operands), allocated on first use
+  float *d_Kp = nullptr, *d_Vp = nullptr, *d_Qp = nullptr, *d_src = nullptr;
 
   template <typename T>
   int alloc(T** p, size_t n) {
@@ -257,22 +266,6 @@ static int ln_rows(cudaStream_t st, const float* in, int ld_in, const float* g, 
   return 0;
 }
 
-template <int HD>
-static int launch_relpos(cudaStream_t st, const __half* qkv, int ld, const float* rph, const float* rpw, int S, int heads, float* rel) {
-  const int L = 2 * S - 1;
-  const size_t smem = (size_t(2) * L * (HD + 1) + 8 * HD) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAMRS_CUDA_OK(cudaFuncSetAttribute(relpos_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    attr_done = true;
-  }
-  dim3 grid(4096 / 8, heads);
-  relpos_kernel<HD><<<grid, 256, smem, st>>>(qkv, ld, rph, rpw, S, rel);
-  SAMRS_CUDA_OK(cudaGetLastError());
-  count_launch();
-  return 0;
-}
-
 template <int HD, int BX, int QBY, int KBY, int NKT>
 static int launch_attn_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, const AttnParams& p, int num_sms, cudaStream_t st) {
   using C = AttnCfg<HD, BX, QBY, KBY, NKT>;
@@ -290,14 +283,20 @@ static int launch_attn_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, const
 }
 
 // encoder attention of one block: rel-pos terms + tcgen05 attention.  qkv: [4096][3D] fp16.
-static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, const float* rph, const float* rpw, bool global,
-                             __half* out) {
-  const int D = e->D, hd = e->hd, S = global ? 64 : 14;
+static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, const __half* reltab, bool global, __half* out) {
+  const int D = e->D, hd = e->hd;
+  if (hd != 64 && hd != 80) SAMRS_FAIL("head_dim must be 64 or 80");
   {
+    // decomposed rel-pos terms for every (head, token): G = q . [rel_pos_h ; rel_pos_w]^T as one head-batched
+    // tensor-core GEMM (A = the q columns of the qkv activation through a rank-3 tensor map)
     ProfScope ps(PC_RELPOS, st);
-    if (hd == 64) SAMRS_TRY(launch_relpos<64>(st, qkv, 3 * D, rph, rpw, S, e->heads, e->rel));
-    else if (hd == 80) SAMRS_TRY(launch_relpos<80>(st, qkv, 3 * D, rph, rpw, S, e->heads, e->rel));
-    else SAMRS_FAIL("head_dim must be 64 or 80");
+    const int NP = global ? 256 : 64;
+    CUtensorMap tA;
+    SAMRS_TRY(make_tmap_3d(&tA, qkv, uint64_t(hd), uint64_t(e->heads), 4096, uint64_t(hd) * 2, uint64_t(3 * D) * 2, GEMM_BK, 1, GEMM_BM));
+    GemmParams gp;
+    gp.M = 4096; gp.N = NP; gp.K = hd; gp.out = e->rel; gp.ldc = NP; gp.bias = nullptr; gp.res = nullptr; gp.ldr = 0; gp.res_mod = 0;
+    gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f;
+    SAMRS_TRY(launch_gemm_tc(nullptr, 8, reltab, hd, gp, false, 0, e->num_sms, st, global ? 256 : 128, &tA));
   }
   ProfScope ps2(global ? PC_ATTN_GLOB : PC_ATTN_WIN, st);
   AttnParams p;
@@ -357,6 +356,20 @@ __global__ void tile_bias_kernel(const float* __restrict__ b, float* __restrict_
   if (i < C * reps) out[i] = b[i % C];
 }
 
+// rel-pos table for the batched GEMM: rows [0,2S-1) = log2e*rel_pos_h, [2S-1,4S-2) = log2e*rel_pos_w, zero padded
+__global__ void build_reltab_kernel(const float* __restrict__ rph, const float* __restrict__ rpw, int S, int hd, int NP,
+                                    __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= NP * hd) return;
+  const int r = i / hd, c = i % hd, L = 2 * S - 1;
+  float v = 0.f;
+  if (r < L) v = rph[r * hd + c];
+  else if (r < 2 * L) v = rpw[(r - L) * hd + c];
+  out[i] = __float2half_rn(v * 1.4426950408889634f);
+}
+struct Engine;
+static int build_reltab(Engine* e, cudaStream_t st, const float* rph, const float* rpw, int S, __half** out);
+
 static int copy_f32(Engine* e, cudaStream_t st, const float* src, int64_t n, float** dst) {
   SAMRS_TRY(e->alloc(dst, size_t(n)));
   SAMRS_CUDA_OK(cudaMemcpyAsync(*dst, src, size_t(n) * 4, cudaMemcpyDeviceToDevice, st));
@@ -367,6 +380,14 @@ static int to_half(Engine* e, cudaStream_t st, const float* src, int64_t n, __ha
   SAMRS_TRY(e->alloc(dst, size_t(n)));
   const size_t n4 = size_t(n) / 4;
   cast_f32_f16_kernel<<<unsigned((n4 + 255) / 256), 256, 0, st>>>(src, *dst, n4);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+static int build_reltab(Engine* e, cudaStream_t st, const float* rph, const float* rpw, int S, __half** out) {
+  const int NP = (S == 64) ? 256 : 64;
+  SAMRS_TRY(e->alloc(out, size_t(NP) * e->hd));
+  build_reltab_kernel<<<(NP * e->hd + 255) / 256, 256, 0, st>>>(rph, rpw, S, e->hd, NP, *out);
   SAMRS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -418,8 +439,10 @@ static int load_weights_impl(Engine* e, const SrcMap& m, cudaStream_t st) {
     const int S = b.global ? 64 : 14;
     SAMRS_TRY(load_pair(e, st, m, p + "norm1", D64, &b.ln1w, &b.ln1b));
     SAMRS_TRY(load_pair(e, st, m, p + "norm2", D64, &b.ln2w, &b.ln2b));
-    SAMRS_TRY(need(m, p + "attn.rel_pos_h", int64_t(2 * S - 1) * e->hd, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(2 * S - 1) * e->hd, &b.rph));
-    SAMRS_TRY(need(m, p + "attn.rel_pos_w", int64_t(2 * S - 1) * e->hd, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(2 * S - 1) * e->hd, &b.rpw));
+    const float *rph, *rpw;
+    SAMRS_TRY(need(m, p + "attn.rel_pos_h", int64_t(2 * S - 1) * e->hd, &rph));
+    SAMRS_TRY(need(m, p + "attn.rel_pos_w", int64_t(2 * S - 1) * e->hd, &rpw));
+    SAMRS_TRY(build_reltab(e, st, rph, rpw, S, &b.reltab));
     SAMRS_TRY(need(m, p + "attn.qkv.weight", 3 * D64 * D64, &s));             SAMRS_TRY(to_half(e, st, s, 3 * D64 * D64, &b.wqkv));
     const float* bqkv;
     SAMRS_TRY(need(m, p + "attn.qkv.bias", 3 * D64, &bqkv));
@@ -505,6 +528,41 @@ static int load_weights_impl(Engine* e, const SrcMap& m, cudaStream_t st) {
     SAMRS_TRY(e->alloc(&e->pek[i], size_t(4096) * 128));
     SAMRS_TRY(sgemm(st, e->dense_pe, 256, pw[i], 256, e->pek[i], 128, nullptr, nullptr, 0, 0, 4096, 128, 256, 0));
   }
+  // tensor-core decoder GEMMs (3-term split fp16): concatenated along N
+  //   P1 = keys(l0) -> [K(l1 t2i) | V(l1 t2i) | Q(l1 i2t)]      N = 384
+  //   P2 = keys(l1) -> [K(final)  | V(final)  | ConvT1 (4x64)]  N = 512
+  //   O0 / O1 = out_proj of the image->token attention of layer 0 / 1   N = 256, K = 128
+  const float WS = 256.0f;
+  auto split_into = [&](const float* w, int N, int K, __half* dst) {
+    split_weight_kernel<<<(N * K + 255) / 256, 256, 0, st>>>(w, N, K, WS, dst);
+  };
+  SAMRS_TRY(e->alloc(&e->wd_p1, size_t(384) * 768));
+  SAMRS_TRY(e->alloc(&e->wd_p2, size_t(512) * 768));
+  SAMRS_TRY(e->alloc(&e->wd_o0, size_t(256) * 384));
+  SAMRS_TRY(e->alloc(&e->wd_o1, size_t(256) * 384));
+  split_into(e->dl[1].t2i.wk, 128, 256, e->wd_p1);
+  split_into(e->dl[1].t2i.wv, 128, 256, e->wd_p1 + size_t(128) * 768);
+  split_into(e->dl[1].i2t.wq, 128, 256, e->wd_p1 + size_t(256) * 768);
+  split_into(e->final_attn.wk, 128, 256, e->wd_p2);
+  split_into(e->final_attn.wv, 128, 256, e->wd_p2 + size_t(128) * 768);
+  split_into(e->up_w1r, 256, 256, e->wd_p2 + size_t(256) * 768);
+  split_into(e->dl[0].i2t.wo, 256, 128, e->wd_o0);
+  split_into(e->dl[1].i2t.wo, 256, 128, e->wd_o1);
+  SAMRS_TRY(e->alloc(&e->bias_p1, 384));
+  SAMRS_TRY(e->alloc(&e->bias_p2, 512));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->bias_p1, e->dl[1].t2i.bk, 512, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->bias_p1 + 128, e->dl[1].t2i.bv, 512, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->bias_p1 + 256, e->dl[1].i2t.bq, 512, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->bias_p2, e->final_attn.bk, 512, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->bias_p2 + 128, e->final_attn.bv, 512, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->bias_p2 + 256, e->up_b1r, 1024, cudaMemcpyDeviceToDevice, st));
+  SAMRS_TRY(e->alloc(&e->R1, size_t(4096) * 384));
+  SAMRS_TRY(e->alloc(&e->R2, size_t(4096) * 512));
+  SAMRS_CUDA_OK(cudaMemsetAsync(e->R1, 0, size_t(4096) * 384 * 4, st));
+  SAMRS_CUDA_OK(cudaMemsetAsync(e->R2, 0, size_t(4096) * 512 * 4, st));
+  SAMRS_CUDA_OK(cudaMemcpy2DAsync(e->R1, 384 * 4, e->pek[2], 128 * 4, 128 * 4, 4096, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpy2DAsync(e->R1 + 256, 384 * 4, e->pek[3], 128 * 4, 128 * 4, 4096, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpy2DAsync(e->R2, 512 * 4, e->pek[4], 128 * 4, 128 * 4, 4096, cudaMemcpyDeviceToDevice, st));
   SAMRS_CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -515,7 +573,7 @@ static int alloc_activations(Engine* e) {
   SAMRS_TRY(e->alloc(&e->x, T * D));
   SAMRS_TRY(e->alloc(&e->xn, T * D));
   SAMRS_TRY(e->alloc(&e->qkv, T * 3 * D));
-  SAMRS_TRY(e->alloc(&e->rel, size_t(e->heads) * T * 128));
+  SAMRS_TRY(e->alloc(&e->rel, size_t(e->heads) * T * 256));
   SAMRS_TRY(e->alloc(&e->attn_o, T * D));
   SAMRS_TRY(e->alloc(&e->hid, T * 4 * D));
   SAMRS_TRY(e->alloc(&e->x16, T * D));
@@ -549,12 +607,9 @@ static int ensure_decoder_scratch(Engine* e, int B) {
   SAMRS_TRY(e->alloc(&e->d_tmp128c, c * TT * 128));
   SAMRS_TRY(e->alloc(&e->d_mlp, c * TT * 2048));
   SAMRS_TRY(e->alloc(&e->d_keys, c * 4096 * 256));
-  SAMRS_TRY(e->alloc(&e->d_io, c * 4096 * 128));
-  SAMRS_TRY(e->alloc(&e->d_Kp, c * 4096 * 128));
-  SAMRS_TRY(e->alloc(&e->d_Vp, c * 4096 * 128));
-  SAMRS_TRY(e->alloc(&e->d_Qp, c * 4096 * 128));
-  SAMRS_TRY(e->alloc(&e->d_u1, c * 4096 * 256));
-  SAMRS_TRY(e->alloc(&e->d_src, c * 4096 * 256));
+  SAMRS_TRY(e->alloc(&e->d_P, c * 4096 * 512));
+  SAMRS_TRY(e->alloc(&e->d_keysA, c * 4096 * 768));
+  SAMRS_TRY(e->alloc(&e->d_ioA, c * 4096 * 384));
   SAMRS_TRY(e->alloc(&e->d_hyper, c * 4 * 32));
   SAMRS_TRY(e->alloc(&e->d_hy_t, c * 256));
   SAMRS_TRY(e->alloc(&e->d_hy_a, c * 256));
@@ -562,6 +617,19 @@ static int ensure_decoder_scratch(Engine* e, int B) {
   SAMRS_TRY(e->alloc(&e->d_iou_all, c * 4));
   SAMRS_TRY(e->alloc(&e->d_low, c * 3 * 65536));
   e->dec_cap = cap;
+  return 0;
+}
+
+static int ensure_mask_scratch(Engine* e, int B) {
+  if (B <= e->mask_cap) return 0;
+  int cap = e->mask_cap ? e->mask_cap : 8;
+  while (cap < B) cap *= 2;
+  const size_t c = cap;
+  SAMRS_TRY(e->alloc(&e->d_Kp, c * 4096 * 128));
+  SAMRS_TRY(e->alloc(&e->d_Vp, c * 4096 * 128));
+  SAMRS_TRY(e->alloc(&e->d_Qp, c * 4096 * 128));
+  SAMRS_TRY(e->alloc(&e->d_src, c * 4096 * 256));
+  e->mask_cap = cap;
   return 0;
 }
 
@@ -573,6 +641,7 @@ static int gemm_enc(Engine* e, cudaStream_t st, const __half* A, int lda, const 
   p.out = out; p.ldc = ldc;
   p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.tiles_m = p.tiles_n = 0;
+  p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f;
   ProfScope ps(PC_GEMM, st);
   return launch_gemm_tc(A, lda, W, K, p, out_half, act, e->num_sms, st, 0);
 }
@@ -603,7 +672,7 @@ static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, flo
     const BlockWeights& b = e->blocks[i];
     { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln1w, b.ln1b, 1e-6f, e->xn, D, T, D))); }
     SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.wqkv, T, 3 * D, D, e->qkv, 3 * D, true, b.bqkv_eff, nullptr, 0, 0, 0));
-    SAMRS_TRY(encoder_attention(e, st, e->qkv, b.rph, b.rpw, b.global, e->attn_o));
+    SAMRS_TRY(encoder_attention(e, st, e->qkv, b.reltab, b.global, e->attn_o));
     SAMRS_TRY(gemm_enc(e, st, e->attn_o, D, b.wproj, T, D, D, e->x, D, false, b.bproj_eff, e->x, D, 0, 0));
     { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln2w, b.ln2b, 1e-6f, e->xn, D, T, D))); }
     SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.w1, T, 4 * D, D, e->hid, 4 * D, true, b.b1, nullptr, 0, 0, 1));
@@ -628,6 +697,15 @@ static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, flo
 }
 
 // ------------------------------------------------------------------ decoder
+// C = A' W'^T / 256 + bias + R : 3-term split-fp16 product on the tcgen05 GEMM (near-fp32 accuracy)
+static int gemm_dec(Engine* e, cudaStream_t st, const __half* A3, const __half* W3, int M, int N, int K3, float* out, int ldc,
+                    const float* bias, const float* res, int ldr, int res_mod) {
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K3; p.out = out; p.ldc = ldc; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
+  p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f;
+  return launch_gemm_tc(A3, K3, W3, K3, p, false, 0, e->num_sms, st, 0);
+}
+
 static int add2(cudaStream_t st, const float* a, const float* b, float* out, size_t n) {
   // out = a + b (elementwise, same shape) via the row-vector kernel with C = n
   if (out != a) SAMRS_CUDA_OK(cudaMemcpyAsync(out, a, n * 4, cudaMemcpyDeviceToDevice, st));
@@ -676,6 +754,7 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
   size_t kv_stride = 0;
   int src_mod = 4096;
   if (mask_in) {
+    SAMRS_TRY(ensure_mask_scratch(e, B));
     MaskEmbedParams mp{mask_in, e->md_w0, e->md_b0, e->md_g1, e->md_be1, e->md_w3, e->md_b3, e->md_g4, e->md_be4, e->md_w6, e->md_b6,
                        e->feat_tok, e->d_src};
     mask_embed_src_kernel<<<(B * 4096 + 127) / 128, 128, 0, st>>>(mp, B);
@@ -692,13 +771,14 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
 
   float* queries = e->d_q;
   float* qpl = e->d_tmp256d;          // queries + query_pe (scratch; token_attention uses a..d before we need it again)
+  const int M4 = B * 4096;
+  const unsigned ln_blocks = unsigned((size_t(M4) * 32 + 255) / 256);
   for (int layer = 0; layer < 2; ++layer) {
     const DecLayer& L = e->dl[layer];
     // (1) token self-attention (transformer.py:155-161)
     if (layer == 0) {
       SAMRS_TRY(token_attention(e, st, L.self_attn, e->d_tok0, e->d_tok0, e->d_tok0, BT, T, B, queries, nullptr));
     } else {
-      // q = k = queries + pe, v = queries, residual
       float* qpe = e->d_mlp;            // reuse the MLP scratch as a [BT,256] temporary
       SAMRS_TRY(add2(st, queries, e->d_tok0, qpe, size_t(BT) * 256));
       SAMRS_TRY(token_attention(e, st, L.self_attn, qpe, qpe, queries, BT, T, B, queries, queries));
@@ -707,14 +787,13 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
     // (2) tokens -> image (transformer.py:164-168)
     SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, L.t2i.wq, 256, e->d_tmp128a, 128, L.t2i.bq, nullptr, 0, 0, BT, 128, 256, 0));
-    const float *Kl = K0, *Vl = V0;
-    size_t kvs = kv_stride;
-    if (layer == 1) {
-      SAMRS_TRY(sgemm(st, e->d_keys, 256, L.t2i.wk, 256, e->d_Kp, 128, L.t2i.bk, e->pek[2], 128, 4096, B * 4096, 128, 256, 0));
-      SAMRS_TRY(sgemm(st, e->d_keys, 256, L.t2i.wv, 256, e->d_Vp, 128, L.t2i.bv, nullptr, 0, 0, B * 4096, 128, 256, 0));
-      Kl = e->d_Kp; Vl = e->d_Vp; kvs = size_t(4096) * 128;
+    if (layer == 0) {
+      t2i_attn_kernel<<<dim3(B, 8, T), 256, 0, st>>>(e->d_tmp128a, K0, V0, 128, kv_stride, e->d_tmp128b, T);
+    } else {
+      // K | V | Q(i2t) projections of the per-prompt image tokens in one tensor-core GEMM
+      SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p1, M4, 384, 768, e->d_P, 384, e->bias_p1, e->R1, 384, 4096));
+      t2i_attn_kernel<<<dim3(B, 8, T), 256, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 384, size_t(4096) * 384, e->d_tmp128b, T);
     }
-    t2i_attn_kernel<<<dim3(B, 8), 256, 0, st>>>(e->d_tmp128a, Kl, Vl, kvs, e->d_tmp128b, T);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
     SAMRS_TRY(sgemm(st, e->d_tmp128b, 128, L.t2i.wo, 128, queries, 256, L.t2i.bo, queries, 256, 0, BT, 256, 128, 0));
@@ -727,29 +806,29 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
     SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, L.i2t.wk, 256, e->d_tmp128a, 128, L.i2t.bk, nullptr, 0, 0, BT, 128, 256, 0));
     SAMRS_TRY(sgemm(st, queries, 256, L.i2t.wv, 256, e->d_tmp128b, 128, L.i2t.bv, nullptr, 0, 0, BT, 128, 256, 0));
-    const float* Ql = Qi0;
-    size_t qs = kv_stride;
-    if (layer == 1) {
-      SAMRS_TRY(sgemm(st, e->d_keys, 256, L.i2t.wq, 256, e->d_Qp, 128, L.i2t.bq, e->pek[3], 128, 4096, B * 4096, 128, 256, 0));
-      Ql = e->d_Qp; qs = size_t(4096) * 128;
-    }
-    i2t_attn_kernel<<<dim3(4096 * 8 / 256, B), 256, size_t(2) * T * 128 * 4, st>>>(Ql, qs, e->d_tmp128a, e->d_tmp128b, e->d_io, T);
+    if (layer == 0)
+      i2t_attn_kernel<<<dim3(4096 * 8 / 256, B), 256, size_t(2) * T * 128 * 4, st>>>(Qi0, 128, kv_stride, e->d_tmp128a, e->d_tmp128b, e->d_ioA, T);
+    else
+      i2t_attn_kernel<<<dim3(4096 * 8 / 256, B), 256, size_t(2) * T * 128 * 4, st>>>(e->d_P + 256, 384, size_t(4096) * 384, e->d_tmp128a,
+                                                                                      e->d_tmp128b, e->d_ioA, T);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
+    // keys = norm4(keys + out_proj(attn)); layer 0's `keys` is src (shared or per prompt)
     if (layer == 0)
-      SAMRS_TRY(sgemm(st, e->d_io, 128, L.i2t.wo, 128, e->d_keys, 256, L.i2t.bo, src, 256, src_mod, B * 4096, 256, 128, 0));
+      SAMRS_TRY(gemm_dec(e, st, e->d_ioA, e->wd_o0, M4, 256, 384, e->d_keys, 256, L.i2t.bo, src, 256, src_mod));
     else
-      SAMRS_TRY(sgemm(st, e->d_io, 128, L.i2t.wo, 128, e->d_keys, 256, L.i2t.bo, e->d_keys, 256, 0, B * 4096, 256, 128, 0));
-    SAMRS_TRY((ln_rows<float, 0>(st, e->d_keys, 256, L.n4w, L.n4b, 1e-5f, e->d_keys, 256, B * 4096, 256)));
+      SAMRS_TRY(gemm_dec(e, st, e->d_ioA, e->wd_o1, M4, 256, 384, e->d_keys, 256, L.i2t.bo, e->d_keys, 256, 0));
+    ln256_split_kernel<<<ln_blocks, 256, 0, st>>>(e->d_keys, L.n4w, L.n4b, 1e-5f, layer == 0 ? e->d_keys : nullptr, e->d_keysA, M4);
+    SAMRS_CUDA_OK(cudaGetLastError());
+    count_launch();
   }
-  // final tokens -> image attention (transformer.py:99-104)
+  // final tokens -> image attention (transformer.py:99-104); its K | V projections share one GEMM with ConvT1
   {
     const DecAttn& a = e->final_attn;
     SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, a.wq, 256, e->d_tmp128a, 128, a.bq, nullptr, 0, 0, BT, 128, 256, 0));
-    SAMRS_TRY(sgemm(st, e->d_keys, 256, a.wk, 256, e->d_Kp, 128, a.bk, e->pek[4], 128, 4096, B * 4096, 128, 256, 0));
-    SAMRS_TRY(sgemm(st, e->d_keys, 256, a.wv, 256, e->d_Vp, 128, a.bv, nullptr, 0, 0, B * 4096, 128, 256, 0));
-    t2i_attn_kernel<<<dim3(B, 8), 256, 0, st>>>(e->d_tmp128a, e->d_Kp, e->d_Vp, size_t(4096) * 128, e->d_tmp128b, T);
+    SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p2, M4, 512, 768, e->d_P, 512, e->bias_p2, e->R2, 512, 4096));
+    t2i_attn_kernel<<<dim3(B, 8, T), 256, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 512, size_t(4096) * 512, e->d_tmp128b, T);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
     SAMRS_TRY(sgemm(st, e->d_tmp128b, 128, a.wo, 128, queries, 256, a.bo, queries, 256, 0, BT, 256, 128, 0));
@@ -774,12 +853,13 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
   // last layer restricted to the returned slice: rows m_first .. m_first+NM-1 of the (4,256) weight
   SAMRS_TRY(sgemm(st, e->d_hy_b, 256, e->iou_head.w[2] + m_first * 256, 256, iou_out, NM, e->iou_head.b[2] + m_first, nullptr, 0, 0, B, NM,
                   256, 0));
-  // upscaling: ConvT1 as GEMM -> LN2d+GELU on 64-channel rows -> fused ConvT2+GELU+hyper product
-  SAMRS_TRY(sgemm(st, e->d_keys, 256, e->up_w1r, 256, e->d_u1, 256, e->up_b1r, nullptr, 0, 0, B * 4096, 256, 256, 0));
-  SAMRS_TRY((ln_rows<float, 1>(st, e->d_u1, 64, e->up_lnw, e->up_lnb, 1e-6f, e->d_u1, 64, B * 16384, 64)));
+  // upscaling: ConvT1 columns of P2 -> LN2d+GELU per 64-channel group (in place) -> fused ConvT2+GELU+hyper product
+  ln64_gelu_grouped_kernel<<<unsigned((size_t(M4) * 4 * 16 + 255) / 256), 256, 0, st>>>(e->d_P, 512, 256, e->up_lnw, e->up_lnb, M4);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
   const unsigned ublocks = unsigned((size_t(B) * 16384 + 127) / 128);
-  if (NM == 1) upscale2_hyper_kernel<1><<<ublocks, 128, 0, st>>>(e->d_u1, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
-  else upscale2_hyper_kernel<3><<<ublocks, 128, 0, st>>>(e->d_u1, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
+  if (NM == 1) upscale2_hyper_kernel<1><<<ublocks, 128, 0, st>>>(e->d_P + 256, 512, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
+  else upscale2_hyper_kernel<3><<<ublocks, 128, 0, st>>>(e->d_P + 256, 512, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -981,6 +1061,7 @@ int samrs_test_gemm(void* engine, const void* A, const void* B, int M, int N, in
   LaunchScope ls(e);
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldc = N; p.bias = bias; p.res = res; p.ldr = N; p.res_mod = 0; p.tiles_m = p.tiles_n = 0;
+  p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f;
   return set_err(e, launch_gemm_tc(static_cast<const __half*>(A), K, static_cast<const __half*>(B), K, p, out_half != 0, act_gelu, e->num_sms,
                                    static_cast<cudaStream_t>(stream), force_bn));
 }
@@ -990,8 +1071,11 @@ int samrs_test_attention(void* engine, const void* qkv, const float* rph, const 
   if (!e) return 1;
   cudaSetDevice(e->device);
   LaunchScope ls(e);
-  return set_err(e, encoder_attention(e, static_cast<cudaStream_t>(stream), static_cast<const __half*>(qkv), rph, rpw, global_block != 0,
-                                      static_cast<__half*>(out)));
+  __half* tab = nullptr;
+  int rc = build_reltab(e, static_cast<cudaStream_t>(stream), rph, rpw, global_block ? 64 : 14, &tab);
+  if (rc == 0) rc = encoder_attention(e, static_cast<cudaStream_t>(stream), static_cast<const __half*>(qkv), tab, global_block != 0,
+                                      static_cast<__half*>(out));
+  return set_err(e, rc);
 }
 
 int samrs_test_sgemm(void* engine, const float* A, const float* W, float* C, const float* bias, int M, int N, int K, int act, void* stream) {

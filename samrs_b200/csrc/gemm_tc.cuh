@@ -25,6 +25,10 @@ struct GemmParams {
   int ldr;
   int res_mod;          // residual row = m % res_mod (0 -> m)
   int tiles_m, tiles_n;
+  int batch;            // >= 1: independent problems sharing B; A is then a rank-3 tensor map (k, batch, m)
+  int a_rank3;
+  long long out_batch_stride;   // elements between consecutive batch outputs
+  float out_scale;      // accumulator is multiplied by this before bias/residual (split-weight scaling); 0 -> 1
 };
 
 constexpr int GEMM_BM = 128;
@@ -57,7 +61,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int num_tiles = tiles_mn * p.batch;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -86,14 +91,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t % p.tiles_m) * GEMM_BM;
-        const int n0 = (t / p.tiles_m) * BN;
+        const int bt = t / tiles_mn, tt = t % tiles_mn;
+        const int m0 = (tt % p.tiles_m) * GEMM_BM;
+        const int n0 = (tt / p.tiles_m) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + GEMM_BM * 128;
           mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          tma_load_2d(sa, &tmA, &full[stage], kb * GEMM_BK, m0);
+          if (p.a_rank3) tma_load_3d(sa, &tmA, &full[stage], kb * GEMM_BK, bt, m0);
+          else tma_load_2d(sa, &tmA, &full[stage], kb * GEMM_BK, m0);
           tma_load_2d(sb, &tmB, &full[stage], kb * GEMM_BK, n0);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
@@ -134,11 +141,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp >= 4) {
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                       // TMEM lane quadrant of this warp
+    const float oscale = (p.out_scale != 0.f) ? p.out_scale : 1.0f;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t % p.tiles_m) * GEMM_BM;
-      const int n0 = (t / p.tiles_m) * BN;
+      const int bt = t / tiles_mn, tt = t % tiles_mn;
+      const int m0 = (tt % p.tiles_m) * GEMM_BM;
+      const int n0 = (tt / p.tiles_m) * BN;
       const int row = m0 + q * 32 + lane;
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
@@ -155,7 +164,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (row < p.M && col0 < p.N) {
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * oscale;
           const bool fullchunk = (col0 + 32 <= p.N);
           if (p.bias != nullptr) {
             if (fullchunk) {
@@ -186,7 +195,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
           }
           if (OUT_HALF) {
-            __half* o = reinterpret_cast<__half*>(p.out) + size_t(row) * p.ldc + col0;
+            __half* o = reinterpret_cast<__half*>(p.out) + size_t(bt) * p.out_batch_stride + size_t(row) * p.ldc + col0;
             if (fullchunk) {
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
@@ -206,7 +215,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (col0 + j < p.N) o[j] = __float2half_rn(f[j]);
             }
           } else {
-            float* o = reinterpret_cast<float*>(p.out) + size_t(row) * p.ldc + col0;
+            float* o = reinterpret_cast<float*>(p.out) + size_t(bt) * p.out_batch_stride + size_t(row) * p.ldc + col0;
             if (fullchunk) {
 #pragma unroll
               for (int j = 0; j < 32; j += 4)
@@ -237,6 +246,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // Host-side launcher: picks the N tile that wastes the fewest SM-waves for this shape.
 int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const GemmParams& p, bool out_half, int act,
-                   int num_sms, cudaStream_t stream, int force_bn = 0);
+                   int num_sms, cudaStream_t stream, int force_bn = 0, const CUtensorMap* a_map_rank3 = nullptr);
 
 }  // namespace samrs

@@ -112,46 +112,6 @@ __global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __rest
 }
 
 // ------------------------------------------------------------------------------------------------
-// Decomposed relative-position terms (SA/modeling/image_encoder.py:325-361, get_rel_pos :292-322):
-//   rel_h[q, kh] = q . rel_pos_h[qh - kh + S - 1],  rel_w[q, kw] = q . rel_pos_w[qw - kw + S - 1]
-// with the UNSCALED q, S = 14 (window-local coordinates) or 64 (global).
-// Output: rel[head][token][2*S] fp32, pre-multiplied by log2(e) for the exp2-domain softmax.
-// One block per (8 tokens, head); the two tables are staged in shared memory with a +1 row pad.
-// ------------------------------------------------------------------------------------------------
-template <int HD>
-__global__ void relpos_kernel(const __half* __restrict__ qkv, int ld_qkv, const float* __restrict__ rph,
-                              const float* __restrict__ rpw, int S, float* __restrict__ rel) {
-  extern __shared__ float sm[];
-  constexpr int TOK = 8;
-  const int L = 2 * S - 1;
-  float* th = sm;                    // [L][HD+1]
-  float* tw = th + L * (HD + 1);     // [L][HD+1]
-  float* sq = tw + L * (HD + 1);     // [TOK][HD]
-  const int head = blockIdx.y;
-  const int tok0 = blockIdx.x * TOK;
-  for (int i = threadIdx.x; i < L * HD; i += blockDim.x) {
-    th[(i / HD) * (HD + 1) + i % HD] = rph[i];
-    tw[(i / HD) * (HD + 1) + i % HD] = rpw[i];
-  }
-  for (int i = threadIdx.x; i < TOK * HD; i += blockDim.x)
-    sq[i] = __half2float(qkv[size_t(tok0 + i / HD) * ld_qkv + head * HD + i % HD]);
-  __syncthreads();
-  const float LOG2E = 1.4426950408889634f;
-  for (int o = threadIdx.x; o < TOK * 2 * S; o += blockDim.x) {
-    const int t = o / (2 * S), j = o % (2 * S);
-    const int token = tok0 + t;
-    const int y = token >> 6, x = token & 63;
-    const int qh = (S == 64) ? y : (y % 14), qw = (S == 64) ? x : (x % 14);
-    const float* tab = (j < S) ? th + (qh - j + S - 1) * (HD + 1) : tw + (qw - (j - S) + S - 1) * (HD + 1);
-    const float* qv = sq + t * HD;
-    float acc = 0.f;
-#pragma unroll 8
-    for (int c = 0; c < HD; ++c) acc = fmaf(qv[c], tab[c], acc);
-    rel[(size_t(head) * 4096 + token) * (2 * S) + j] = acc * LOG2E;
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // Neck helpers (SA/modeling/image_encoder.py:88-104): 3x3/pad-1 conv as im2col'ed GEMM, and the final
 // LayerNorm2d written both token-major (decoder input) and NCHW (the `features` tensor of the API).
 // ------------------------------------------------------------------------------------------------
@@ -470,84 +430,87 @@ __global__ void tok_self_attn_kernel(const float* __restrict__ q, const float* _
   }
 }
 
-// (2) token -> image cross attention: q [B][T][128]; K,V [B or 1][4096][128] (kv_bstride 0 = shared);
-//     8 heads x 16.  One block per (prompt, head), 256 threads x 16 keys each, softmax over 4096 keys.
+// (2) token -> image cross attention: q [B][T][128]; K,V rows of `ld` floats, prompt stride kv_bstride
+//     (0 = shared by all prompts); 8 heads x 16.  One block per (prompt, head, query token): 256 threads x 16 keys,
+//     softmax over the 4096 image keys with one block-wide (max, sum, weighted-V) combine.
 __global__ void __launch_bounds__(256)
-t2i_attn_kernel(const float* __restrict__ q, const float* __restrict__ K, const float* __restrict__ V,
+t2i_attn_kernel(const float* __restrict__ q, const float* __restrict__ K, const float* __restrict__ V, int ld,
                 size_t kv_bstride, float* __restrict__ out, int T) {
-  const int b = blockIdx.x, h = blockIdx.y, tid = threadIdx.x;
+  const int b = blockIdx.x, h = blockIdx.y, t = blockIdx.z, tid = threadIdx.x;
   const float* Kb = K + size_t(b) * kv_bstride + h * 16;
   const float* Vb = V + size_t(b) * kv_bstride + h * 16;
   __shared__ float red[8][18];
-  for (int t = 0; t < T; ++t) {
-    float qv[16];
+  float qv[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) qv[c] = q[(size_t(b) * T + t) * 128 + h * 16 + c];
-    float s[16];
-    float m = -INFINITY;
+  for (int c = 0; c < 16; ++c) qv[c] = q[(size_t(b) * T + t) * 128 + h * 16 + c];
+  float s[16];
+  float m = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float4* kr = reinterpret_cast<const float4*>(Kb + size_t(tid + 256 * i) * 128);
-      const float4 k0 = kr[0], k1 = kr[1], k2 = kr[2], k3 = kr[3];
-      float a = qv[0] * k0.x;
-      a = fmaf(qv[1], k0.y, a); a = fmaf(qv[2], k0.z, a); a = fmaf(qv[3], k0.w, a);
-      a = fmaf(qv[4], k1.x, a); a = fmaf(qv[5], k1.y, a); a = fmaf(qv[6], k1.z, a); a = fmaf(qv[7], k1.w, a);
-      a = fmaf(qv[8], k2.x, a); a = fmaf(qv[9], k2.y, a); a = fmaf(qv[10], k2.z, a); a = fmaf(qv[11], k2.w, a);
-      a = fmaf(qv[12], k3.x, a); a = fmaf(qv[13], k3.y, a); a = fmaf(qv[14], k3.z, a); a = fmaf(qv[15], k3.w, a);
-      s[i] = a * 0.25f;                     // / sqrt(16)
-      m = fmaxf(m, s[i]);
-    }
-    // block max
+  for (int i = 0; i < 16; ++i) {
+    const float4* kr = reinterpret_cast<const float4*>(Kb + size_t(tid + 256 * i) * ld);
+    const float4 k0 = kr[0], k1 = kr[1], k2 = kr[2], k3 = kr[3];
+    float a = qv[0] * k0.x;
+    a = fmaf(qv[1], k0.y, a); a = fmaf(qv[2], k0.z, a); a = fmaf(qv[3], k0.w, a);
+    a = fmaf(qv[4], k1.x, a); a = fmaf(qv[5], k1.y, a); a = fmaf(qv[6], k1.z, a); a = fmaf(qv[7], k1.w, a);
+    a = fmaf(qv[8], k2.x, a); a = fmaf(qv[9], k2.y, a); a = fmaf(qv[10], k2.z, a); a = fmaf(qv[11], k2.w, a);
+    a = fmaf(qv[12], k3.x, a); a = fmaf(qv[13], k3.y, a); a = fmaf(qv[14], k3.z, a); a = fmaf(qv[15], k3.w, a);
+    s[i] = a * 0.25f;                     // / sqrt(16)
+    m = fmaxf(m, s[i]);
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((tid & 31) == 0) red[tid >> 5][0] = m;
-    __syncthreads();
-    m = red[0][0];
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((tid & 31) == 0) red[tid >> 5][17] = m;
+  __syncthreads();
+  m = red[0][17];
 #pragma unroll
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w][0]);
-    __syncthreads();
-    float l = 0.f;
-    float acc[16];
+  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w][17]);
+  float l = 0.f;
+  float acc[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-      const float pexp = expf(s[i] - m);
-      l += pexp;
-      const float4* vr = reinterpret_cast<const float4*>(Vb + size_t(tid + 256 * i) * 128);
-      const float4 v0 = vr[0], v1 = vr[1], v2 = vr[2], v3 = vr[3];
-      acc[0] = fmaf(pexp, v0.x, acc[0]); acc[1] = fmaf(pexp, v0.y, acc[1]); acc[2] = fmaf(pexp, v0.z, acc[2]); acc[3] = fmaf(pexp, v0.w, acc[3]);
-      acc[4] = fmaf(pexp, v1.x, acc[4]); acc[5] = fmaf(pexp, v1.y, acc[5]); acc[6] = fmaf(pexp, v1.z, acc[6]); acc[7] = fmaf(pexp, v1.w, acc[7]);
-      acc[8] = fmaf(pexp, v2.x, acc[8]); acc[9] = fmaf(pexp, v2.y, acc[9]); acc[10] = fmaf(pexp, v2.z, acc[10]); acc[11] = fmaf(pexp, v2.w, acc[11]);
-      acc[12] = fmaf(pexp, v3.x, acc[12]); acc[13] = fmaf(pexp, v3.y, acc[13]); acc[14] = fmaf(pexp, v3.z, acc[14]); acc[15] = fmaf(pexp, v3.w, acc[15]);
-    }
+  for (int i = 0; i < 16; ++i) {
+    const float pexp = expf(s[i] - m);
+    l += pexp;
+    const float4* vr = reinterpret_cast<const float4*>(Vb + size_t(tid + 256 * i) * ld);
+    const float4 v0 = vr[0], v1 = vr[1], v2 = vr[2], v3 = vr[3];
+    acc[0] = fmaf(pexp, v0.x, acc[0]); acc[1] = fmaf(pexp, v0.y, acc[1]); acc[2] = fmaf(pexp, v0.z, acc[2]); acc[3] = fmaf(pexp, v0.w, acc[3]);
+    acc[4] = fmaf(pexp, v1.x, acc[4]); acc[5] = fmaf(pexp, v1.y, acc[5]); acc[6] = fmaf(pexp, v1.z, acc[6]); acc[7] = fmaf(pexp, v1.w, acc[7]);
+    acc[8] = fmaf(pexp, v2.x, acc[8]); acc[9] = fmaf(pexp, v2.y, acc[9]); acc[10] = fmaf(pexp, v2.z, acc[10]); acc[11] = fmaf(pexp, v2.w, acc[11]);
+    acc[12] = fmaf(pexp, v3.x, acc[12]); acc[13] = fmaf(pexp, v3.y, acc[13]); acc[14] = fmaf(pexp, v3.z, acc[14]); acc[15] = fmaf(pexp, v3.w, acc[15]);
+  }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      l += __shfl_xor_sync(0xffffffffu, l, o);
+  for (int o = 16; o > 0; o >>= 1) {
+    l += __shfl_xor_sync(0xffffffffu, l, o);
 #pragma unroll
-      for (int c = 0; c < 16; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-    }
-    if ((tid & 31) == 0) {
-      red[tid >> 5][16] = l;
+    for (int c = 0; c < 16; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  }
+  if ((tid & 31) == 0) {
+    red[tid >> 5][16] = l;
 #pragma unroll
-      for (int c = 0; c < 16; ++c) red[tid >> 5][c] = acc[c];
-    }
-    __syncthreads();
-    if (tid < 16) {
-      float num = 0.f, den = 0.f;
+    for (int c = 0; c < 16; ++c) red[tid >> 5][c] = acc[c];
+  }
+  __syncthreads();
+  if (tid < 16) {
+    float num = 0.f, den = 0.f;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) { num += red[w][tid]; den += red[w][16]; }
-      out[(size_t(b) * T + t) * 128 + h * 16 + tid] = num / den;
-    }
-    __syncthreads();
+    for (int w = 0; w < 8; ++w) { num += red[w][tid]; den += red[w][16]; }
+    out[(size_t(b) * T + t) * 128 + h * 16 + tid] = num / den;
   }
 }
 
-// (3) image -> token cross attention: Q [B or 1][4096][128] (q_bstride 0 = shared); k,v [B][T][128];
-//     one thread per (prompt, image token, head); k,v of the prompt staged in smem.
+// split an fp32 value into fp16 hi + lo (hi + lo == v to ~2^-22 relative): operands of the 3-term tensor-core GEMM
+__device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+// (3) image -> token cross attention: Q rows of `ldq` floats, prompt stride q_bstride (0 = shared); k,v [B][T][128];
+//     one thread per (prompt, image token, head); k,v of the prompt staged in smem.  The result feeds the out_proj
+//     tensor-core GEMM, so it is written directly as the split-fp16 operand [B*4096][hi(128) | lo(128) | hi(128)].
 __global__ void __launch_bounds__(256)
-i2t_attn_kernel(const float* __restrict__ Q, size_t q_bstride, const float* __restrict__ k, const float* __restrict__ v,
-                float* __restrict__ out /*[B][4096][128]*/, int T) {
+i2t_attn_kernel(const float* __restrict__ Q, int ldq, size_t q_bstride, const float* __restrict__ k, const float* __restrict__ v,
+                __half* __restrict__ out_split /*[B][4096][384]*/, int T) {
   extern __shared__ float sm[];
   float* sk = sm;
   float* sv = sm + T * 128;
@@ -560,34 +523,114 @@ i2t_attn_kernel(const float* __restrict__ Q, size_t q_bstride, const float* __re
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (token, head)
   if (idx >= 4096 * 8) return;
   const int token = idx >> 3, h = idx & 7;
-  const float4* qr = reinterpret_cast<const float4*>(Q + size_t(b) * q_bstride + size_t(token) * 128 + h * 16);
+  const float4* qr = reinterpret_cast<const float4*>(Q + size_t(b) * q_bstride + size_t(token) * ldq + h * 16);
   const float4 q0 = qr[0], q1 = qr[1], q2 = qr[2], q3 = qr[3];
   const float qv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-  float s[16];
   float m = -INFINITY;
   for (int t = 0; t < T; ++t) {
     float a = 0.f;
 #pragma unroll
     for (int c = 0; c < 16; ++c) a = fmaf(qv[c], sk[t * 128 + h * 16 + c], a);
-    s[t] = a * 0.25f;
-    m = fmaxf(m, s[t]);
+    m = fmaxf(m, a * 0.25f);
   }
   float l = 0.f;
   float acc[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = 0.f;
   for (int t = 0; t < T; ++t) {
-    const float pexp = expf(s[t] - m);
+    float a = 0.f;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) a = fmaf(qv[c], sk[t * 128 + h * 16 + c], a);
+    const float pexp = expf(a * 0.25f - m);
     l += pexp;
 #pragma unroll
     for (int c = 0; c < 16; ++c) acc[c] = fmaf(pexp, sv[t * 128 + h * 16 + c], acc[c]);
   }
   const float inv = 1.0f / l;
-  float4* o = reinterpret_cast<float4*>(out + (size_t(b) * 4096 + token) * 128 + h * 16);
-  o[0] = make_float4(acc[0] * inv, acc[1] * inv, acc[2] * inv, acc[3] * inv);
-  o[1] = make_float4(acc[4] * inv, acc[5] * inv, acc[6] * inv, acc[7] * inv);
-  o[2] = make_float4(acc[8] * inv, acc[9] * inv, acc[10] * inv, acc[11] * inv);
-  o[3] = make_float4(acc[12] * inv, acc[13] * inv, acc[14] * inv, acc[15] * inv);
+  __half hi[16], lo[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) split_f16(acc[c] * inv, hi[c], lo[c]);
+  __half* o = out_split + (size_t(b) * 4096 + token) * 384 + h * 16;
+  reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(hi)[0];
+  reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(hi)[1];
+  reinterpret_cast<uint4*>(o + 128)[0] = reinterpret_cast<uint4*>(lo)[0];
+  reinterpret_cast<uint4*>(o + 128)[1] = reinterpret_cast<uint4*>(lo)[1];
+  reinterpret_cast<uint4*>(o + 256)[0] = reinterpret_cast<uint4*>(hi)[0];
+  reinterpret_cast<uint4*>(o + 256)[1] = reinterpret_cast<uint4*>(hi)[1];
+}
+
+// LayerNorm over 256 channels (decoder norm4, eps 1e-5) writing the fp32 result (optional) and its split-fp16
+// form [hi(256) | lo(256) | hi(256)] for the following tensor-core GEMMs.  One warp per row.
+__global__ void ln256_split_kernel(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                   float eps, float* __restrict__ out_f32, __half* __restrict__ out_split, int rows) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float4* src = reinterpret_cast<const float4*>(in + size_t(row) * 256);
+  const float4 a = src[lane], b = src[lane + 32];
+  float s = (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / 256.0f);
+  float d[8] = {a.x - mean, a.y - mean, a.z - mean, a.w - mean, b.x - mean, b.y - mean, b.z - mean, b.w - mean};
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) q = fmaf(d[i], d[i], q);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * (1.0f / 256.0f) + eps);
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int k = lane + 32 * half;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + k);
+    const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + k);
+    const float y0 = d[4 * half] * rstd * g.x + be.x, y1 = d[4 * half + 1] * rstd * g.y + be.y;
+    const float y2 = d[4 * half + 2] * rstd * g.z + be.z, y3 = d[4 * half + 3] * rstd * g.w + be.w;
+    if (out_f32) reinterpret_cast<float4*>(out_f32 + size_t(row) * 256)[k] = make_float4(y0, y1, y2, y3);
+    __half hi[4], lo[4];
+    split_f16(y0, hi[0], lo[0]); split_f16(y1, hi[1], lo[1]); split_f16(y2, hi[2], lo[2]); split_f16(y3, hi[3], lo[3]);
+    __half* o = out_split + size_t(row) * 768 + 4 * k;
+    *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(hi);
+    *reinterpret_cast<uint2*>(o + 256) = *reinterpret_cast<uint2*>(lo);
+    *reinterpret_cast<uint2*>(o + 512) = *reinterpret_cast<uint2*>(hi);
+  }
+}
+
+// LayerNorm2d(64, eps 1e-6) + GELU of output_upscaling, in place on 64-channel groups laid out as
+// base[row * ld + off + g * 64 + c], g < 4 (the ConvT1 columns of the fused projection GEMM).  Half a warp per group.
+__global__ void ln64_gelu_grouped_kernel(float* __restrict__ base, int ld, int off, const float* __restrict__ gamma,
+                                         const float* __restrict__ beta, int rows) {
+  const int gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;       // (row, group)
+  const int l16 = threadIdx.x & 15;
+  if (gidx >= rows * 4) return;
+  float4* p = reinterpret_cast<float4*>(base + size_t(gidx >> 2) * ld + off + (gidx & 3) * 64) + l16;
+  const float4 a = *p;
+  float s = (a.x + a.y) + (a.z + a.w);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / 64.0f);
+  const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+  float q = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / 64.0f) + 1e-6f);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + l16);
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + l16);
+  *p = make_float4(gelu_erf_f(g.x * (d0 * rstd) + be.x), gelu_erf_f(g.y * (d1 * rstd) + be.y),
+                   gelu_erf_f(g.z * (d2 * rstd) + be.z), gelu_erf_f(g.w * (d3 * rstd) + be.w));
+}
+
+// weight [N][K] fp32 -> split-fp16 [N][3K] = scale * [hi | hi | lo], matching activations stored [hi | lo | hi]
+__global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, float scale, __half* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N * K) return;
+  const int n = i / K, k = i % K;
+  __half hi, lo;
+  split_f16(w[i] * scale, hi, lo);
+  __half* o = out + size_t(n) * 3 * K;
+  o[k] = hi;
+  o[K + k] = hi;
+  o[2 * K + k] = lo;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -599,7 +642,8 @@ i2t_attn_kernel(const float* __restrict__ Q, size_t q_bstride, const float* __re
 // ------------------------------------------------------------------------------------------------
 template <int NM>
 __global__ void __launch_bounds__(128)
-upscale2_hyper_kernel(const float* __restrict__ u1 /*[B][4096][4][64]*/, const float* __restrict__ w2r /*[4][32][64]*/,
+upscale2_hyper_kernel(const float* __restrict__ u1 /*row (b,token) at u1 + (b*4096+token)*ld, 4 groups of 64*/, int ld,
+                      const float* __restrict__ w2r /*[4][32][64]*/,
                       const float* __restrict__ b2, const float* __restrict__ hyper /*[B][NM][32]*/,
                       float* __restrict__ low /*[B][NM][256][256]*/, int B) {
   __shared__ __align__(16) float sw[4 * 32 * 64];
@@ -613,7 +657,7 @@ upscale2_hyper_kernel(const float* __restrict__ u1 /*[B][4096][4][64]*/, const f
   const int token = rem >> 2, d1 = rem & 3;
   const int Y = 2 * (token >> 6) + (d1 >> 1), X = 2 * (token & 63) + (d1 & 1);     // 128x128 position
   float u[64];
-  const float4* src = reinterpret_cast<const float4*>(u1 + idx * 64);
+  const float4* src = reinterpret_cast<const float4*>(u1 + (size_t(b) * 4096 + token) * ld + d1 * 64);
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const float4 t = src[i];

@@ -1,0 +1,12 @@
+#!/bin/bash
+# parity tests (each file in its own process) + bench line
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_kernels.py -q -x 2>&1 | tail -15 > gpurun_out/kernels.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -q -x -s 2>&1 | tail -40 >> gpurun_out/kernels.log
+cat gpurun_out/kernels.log
+python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench.json 2> gpurun_out/bench.err
+tail -5 gpurun_out/bench.err; cat gpurun_out/bench.json
+if [ "$1" == "launches" ]; then
+timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
+  --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu1.log 2>&1
+fi
