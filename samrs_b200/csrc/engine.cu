@@ -11,6 +11,7 @@
 #include "attn_tc.cuh"
 #include "common.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc2.cuh"
 #include "simt.cuh"
 
 namespace samrs {
@@ -95,32 +96,76 @@ static int launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const 
   return 0;
 }
 
+template <int BN, bool OH, int ACT>
+static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, int grid, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAMRS_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<BN, OH, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  gemm_tc2_kernel<BN, OH, ACT><<<grid, 256, Cfg::kSmemBytes, st>>>(tA, tB, p);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// model of one tile's duration in SM clocks: tensor-pipe time vs the L2->SM feed (~50 B/clk/SM measured)
+static double tile_clk(int bn, int K, bool pair) {
+  const double mma = double(bn) * K / 32.0;
+  const double l2 = (128.0 + (pair ? bn / 2.0 : double(bn))) * K * 2.0 / 50.0;
+  return (mma > l2 ? mma : l2) + 600.0;
+}
+
 int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const GemmParams& pin, bool out_half, int act,
                    int num_sms, cudaStream_t stream, int force_bn, const CUtensorMap* a_map_rank3) {
   GemmParams p = pin;
   if (p.batch < 1) p.batch = 1;
   p.a_rank3 = a_map_rank3 ? 1 : 0;
   if (p.K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) SAMRS_FAIL("gemm: K and leading dimensions must be multiples of 8");
-  int bn = force_bn;
-  if (bn == 0) {
-    // choose the N tile with the best useful-work / (waves * tile cost) ratio
+  // force_bn: 0 = choose; 128/160/256 = 1-CTA kernel with that N tile; 1128/1160/1256 = CTA-pair kernel
+  int bn = force_bn % 1000;
+  bool pair = force_bn >= 1000;
+  if (force_bn == 0) {
+    // pick the (kernel, N tile) with the smallest modelled duration = waves x per-tile time
     const int cands[3] = {256, 160, 128};
-    double best = -1.0;
-    for (int i = 0; i < 3; ++i) {
-      const int c = cands[i];
-      const long tm = (p.M + GEMM_BM - 1) / GEMM_BM, tn = (p.N + c - 1) / c;
-      const long waves = (tm * tn * p.batch + num_sms - 1) / num_sms;
-      const double eff = double(p.M) * p.N * p.batch / (double(waves) * num_sms * GEMM_BM * c);
-      if (eff > best + 1e-9) { best = eff; bn = c; }
+    double best = 1e30;
+    for (int pr = 0; pr < 2; ++pr) {
+      static const bool no_pair = getenv("SAMRS_NO_PAIR") != nullptr;
+      if (pr == 1 && (no_pair || p.batch != 1 || a_map_rank3 || p.M < 256 || (num_sms & 1))) continue;
+      for (int i = 0; i < 3; ++i) {
+        const int c = cands[i];
+        const long tm = (p.M + (pr ? 255 : 127)) / (pr ? 256 : 128), tn = (p.N + c - 1) / c;
+        const long units = pr ? num_sms / 2 : num_sms;
+        const long waves = (tm * tn * p.batch + units - 1) / units;
+        const double cost = double(waves) * tile_clk(c, p.K, pr != 0);
+        if (cost < best - 1e-9) { best = cost; bn = c; pair = (pr != 0); }
+      }
     }
   }
-  p.tiles_m = (p.M + GEMM_BM - 1) / GEMM_BM;
+  p.tiles_m = (p.M + (pair ? 255 : 127)) / (pair ? 256 : 128);
   p.tiles_n = (p.N + bn - 1) / bn;
   CUtensorMap tA, tB;
   if (a_map_rank3) tA = *a_map_rank3;
   else SAMRS_TRY(make_tmap_2d(&tA, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, GEMM_BK, GEMM_BM));
-  SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t(bn)));
+  SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t(pair ? bn / 2 : bn)));
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
+  if (pair) {
+    const int pairs = num_sms / 2;
+    const int grid2 = 2 * (tiles < pairs ? tiles : pairs);
+#define SAMRS_GEMM2_CASE(BN_)                                                                       \
+  if (bn == BN_) {                                                                                  \
+    if (out_half && act == 0) return launch_gemm2_inst<BN_, true, 0>(tA, tB, p, grid2, stream);     \
+    if (out_half && act == 1) return launch_gemm2_inst<BN_, true, 1>(tA, tB, p, grid2, stream);     \
+    if (!out_half && act == 0) return launch_gemm2_inst<BN_, false, 0>(tA, tB, p, grid2, stream);   \
+    SAMRS_FAIL("gemm: unsupported epilogue");                                                       \
+  }
+    SAMRS_GEMM2_CASE(256)
+    SAMRS_GEMM2_CASE(160)
+    SAMRS_GEMM2_CASE(128)
+#undef SAMRS_GEMM2_CASE
+    SAMRS_FAIL("gemm: unsupported N tile");
+  }
   const int grid = tiles < num_sms ? tiles : num_sms;
 #define SAMRS_GEMM_CASE(BN_)                                                                        \
   if (bn == BN_) {                                                                                  \
@@ -214,6 +259,9 @@ struct Engine {
   // per-image decoder cache
   float *src0, *K0, *V0, *Qi0;
   float* pp_full = nullptr;            // postprocess scratch for non-1024 sizes
+  float* splitk_ws = nullptr;          // split-K partial sums of the token-side SGEMMs
+  size_t splitk_ws_floats = 0;
+  float* d_t2i_part = nullptr;         // [cap][8][16][8][18] key-chunk partials of the token->image attention
   // decoder scratch (sized for dec_cap prompts)
   int dec_cap = 0;
   float *d_tok0, *d_q, *d_tmp256a, *d_tmp256b, *d_tmp256c, *d_tmp256d, *d_tmp128a, *d_tmp128b, *d_tmp128c, *d_mlp;
@@ -238,10 +286,28 @@ static int set_err(Engine* e, int rc) {
 }
 
 // ------------------------------------------------------------------ small launch helpers
+static float* g_splitk_ws = nullptr;          // split-K workspace of the active engine (set by LaunchScope)
+static size_t g_splitk_ws_floats = 0;
 static int sgemm(cudaStream_t st, const float* A, int lda, const float* W, int ldw, float* C, int ldc, const float* bias,
                  const float* R, int ldr, int rmod, int M, int N, int K, int act) {
   if (K % 16 != 0 || lda % 4 != 0 || ldw % 4 != 0) SAMRS_FAIL("sgemm: K must be a multiple of 16");
   SgemmParams p{A, lda, W, ldw, C, ldc, bias, R, ldr, rmod, M, N, K, act};
+  if (M <= 2048 && K % 64 == 0) {
+    // token-side GEMM: latency-bound, 64-deep k slices; split K >= 1024 across blockIdx.z (deterministic reduce)
+    int splits = 1;
+    if (K >= 1024 && g_splitk_ws && size_t(M) * N * 8 <= g_splitk_ws_floats) splits = 8;
+    const int kps = ((K / splits + 63) / 64) * 64;
+    dim3 grid((M + 63) / 64, (N + 63) / 64, splits);
+    sgemm_small_kernel<<<grid, 256, 0, st>>>(p, kps, splits > 1 ? g_splitk_ws : nullptr);
+    SAMRS_CUDA_OK(cudaGetLastError());
+    count_launch();
+    if (splits > 1) {
+      splitk_reduce_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(p, g_splitk_ws, splits);
+      SAMRS_CUDA_OK(cudaGetLastError());
+      count_launch();
+    }
+    return 0;
+  }
   dim3 grid((M + 127) / 128, (N + 63) / 64);
   sgemm_tn_kernel<<<grid, 256, 0, st>>>(p);
   SAMRS_CUDA_OK(cudaGetLastError());
@@ -587,6 +653,8 @@ static int alloc_activations(Engine* e) {
   SAMRS_TRY(e->alloc(&e->K0, T * 128));
   SAMRS_TRY(e->alloc(&e->V0, T * 128));
   SAMRS_TRY(e->alloc(&e->Qi0, T * 128));
+  e->splitk_ws_floats = size_t(8) * 1024 * 2048;
+  SAMRS_TRY(e->alloc(&e->splitk_ws, e->splitk_ws_floats));
   return 0;
 }
 
@@ -606,6 +674,7 @@ static int ensure_decoder_scratch(Engine* e, int B) {
   SAMRS_TRY(e->alloc(&e->d_tmp128b, c * TT * 128));
   SAMRS_TRY(e->alloc(&e->d_tmp128c, c * TT * 128));
   SAMRS_TRY(e->alloc(&e->d_mlp, c * TT * 2048));
+  SAMRS_TRY(e->alloc(&e->d_t2i_part, c * 8 * 16 * 8 * 18));
   SAMRS_TRY(e->alloc(&e->d_keys, c * 4096 * 256));
   SAMRS_TRY(e->alloc(&e->d_P, c * 4096 * 512));
   SAMRS_TRY(e->alloc(&e->d_keysA, c * 4096 * 768));
@@ -788,14 +857,15 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
     SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, L.t2i.wq, 256, e->d_tmp128a, 128, L.t2i.bq, nullptr, 0, 0, BT, 128, 256, 0));
     if (layer == 0) {
-      t2i_attn_kernel<<<dim3(B, 8, T), 256, 0, st>>>(e->d_tmp128a, K0, V0, 128, kv_stride, e->d_tmp128b, T);
+      t2i_attn_kernel<<<dim3(B, 8, 8), 256, 0, st>>>(e->d_tmp128a, K0, V0, 128, kv_stride, e->d_t2i_part, T);
     } else {
       // K | V | Q(i2t) projections of the per-prompt image tokens in one tensor-core GEMM
       SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p1, M4, 384, 768, e->d_P, 384, e->bias_p1, e->R1, 384, 4096));
-      t2i_attn_kernel<<<dim3(B, 8, T), 256, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 384, size_t(4096) * 384, e->d_tmp128b, T);
+      t2i_attn_kernel<<<dim3(B, 8, 8), 256, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 384, size_t(4096) * 384, e->d_t2i_part, T);
     }
+    t2i_combine_kernel<<<(B * 8 * T * 16 + 255) / 256, 256, 0, st>>>(e->d_t2i_part, e->d_tmp128b, B, T);
     SAMRS_CUDA_OK(cudaGetLastError());
-    count_launch();
+    count_launch(2);
     SAMRS_TRY(sgemm(st, e->d_tmp128b, 128, L.t2i.wo, 128, queries, 256, L.t2i.bo, queries, 256, 0, BT, 256, 128, 0));
     SAMRS_TRY((ln_rows<float, 0>(st, queries, 256, L.n2w, L.n2b, 1e-5f, queries, 256, BT, 256)));
     // (3) token MLP (transformer.py:171-173)
@@ -807,10 +877,10 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
     SAMRS_TRY(sgemm(st, qpl, 256, L.i2t.wk, 256, e->d_tmp128a, 128, L.i2t.bk, nullptr, 0, 0, BT, 128, 256, 0));
     SAMRS_TRY(sgemm(st, queries, 256, L.i2t.wv, 256, e->d_tmp128b, 128, L.i2t.bv, nullptr, 0, 0, BT, 128, 256, 0));
     if (layer == 0)
-      i2t_attn_kernel<<<dim3(4096 * 8 / 256, B), 256, size_t(2) * T * 128 * 4, st>>>(Qi0, 128, kv_stride, e->d_tmp128a, e->d_tmp128b, e->d_ioA, T);
+      i2t_attn_kernel<<<dim3(4096 / 128, B), 128, size_t(2) * T * 128 * 4, st>>>(Qi0, 128, kv_stride, e->d_tmp128a, e->d_tmp128b, e->d_ioA, T);
     else
-      i2t_attn_kernel<<<dim3(4096 * 8 / 256, B), 256, size_t(2) * T * 128 * 4, st>>>(e->d_P + 256, 384, size_t(4096) * 384, e->d_tmp128a,
-                                                                                      e->d_tmp128b, e->d_ioA, T);
+      i2t_attn_kernel<<<dim3(4096 / 128, B), 128, size_t(2) * T * 128 * 4, st>>>(e->d_P + 256, 384, size_t(4096) * 384, e->d_tmp128a,
+                                                                                  e->d_tmp128b, e->d_ioA, T);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
     // keys = norm4(keys + out_proj(attn)); layer 0's `keys` is src (shared or per prompt)
@@ -828,9 +898,10 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
     SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, a.wq, 256, e->d_tmp128a, 128, a.bq, nullptr, 0, 0, BT, 128, 256, 0));
     SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p2, M4, 512, 768, e->d_P, 512, e->bias_p2, e->R2, 512, 4096));
-    t2i_attn_kernel<<<dim3(B, 8, T), 256, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 512, size_t(4096) * 512, e->d_tmp128b, T);
+    t2i_attn_kernel<<<dim3(B, 8, 8), 256, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 512, size_t(4096) * 512, e->d_t2i_part, T);
+    t2i_combine_kernel<<<(B * 8 * T * 16 + 255) / 256, 256, 0, st>>>(e->d_t2i_part, e->d_tmp128b, B, T);
     SAMRS_CUDA_OK(cudaGetLastError());
-    count_launch();
+    count_launch(2);
     SAMRS_TRY(sgemm(st, e->d_tmp128b, 128, a.wo, 128, queries, 256, a.bo, queries, 256, 0, BT, 256, 128, 0));
     SAMRS_TRY((ln_rows<float, 0>(st, queries, 256, e->nfw, e->nfb, 1e-5f, queries, 256, BT, 256)));
   }
@@ -871,8 +942,13 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
 using namespace samrs;
 
 struct LaunchScope {
-  explicit LaunchScope(Engine* e) { g_launch_counter = e ? &e->launches : nullptr; g_prof = e ? &e->prof : nullptr; }
-  ~LaunchScope() { g_launch_counter = nullptr; g_prof = nullptr; }
+  explicit LaunchScope(Engine* e) {
+    g_launch_counter = e ? &e->launches : nullptr;
+    g_prof = e ? &e->prof : nullptr;
+    g_splitk_ws = e ? e->splitk_ws : nullptr;
+    g_splitk_ws_floats = e ? e->splitk_ws_floats : 0;
+  }
+  ~LaunchScope() { g_launch_counter = nullptr; g_prof = nullptr; g_splitk_ws = nullptr; g_splitk_ws_floats = 0; }
 };
 
 extern "C" {

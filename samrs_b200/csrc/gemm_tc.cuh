@@ -44,6 +44,87 @@ struct GemmCfg {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// Epilogue of one accumulator tile for the thread that owns TMEM lane (row): BN fp32 columns -> scale, bias,
+// residual, activation -> fp16 / fp32 global stores (each thread writes contiguous 64- or 128-byte runs of its row).
+template <int BN, bool OUT_HALF, int ACT>
+__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_addr, int row, int n0, int bt, float oscale) {
+      const float* res_row = nullptr;
+        if (p.res != nullptr && row < p.M)
+          res_row = p.res + size_t(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr;
+  #pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(t_addr + uint32_t(c * 32), v);
+          tc_wait_ld();
+          const int col0 = n0 + c * 32;
+          if (row < p.M && col0 < p.N) {
+            float f[32];
+  #pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * oscale;
+            const bool fullchunk = (col0 + 32 <= p.N);
+            if (p.bias != nullptr) {
+              if (fullchunk) {
+  #pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
+                  f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
+              }
+            }
+            if (res_row != nullptr) {
+              if (fullchunk) {
+  #pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                  const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);
+                  f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) f[j] += res_row[col0 + j];
+              }
+            }
+            if (ACT == 1) {
+  #pragma unroll
+              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+            }
+            if (OUT_HALF) {
+              __half* o = reinterpret_cast<__half*>(p.out) + size_t(bt) * p.out_batch_stride + size_t(row) * p.ldc + col0;
+              if (fullchunk) {
+  #pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                  uint4 pk;
+                  __half2 h0 = __floats2half2_rn(f[j], f[j + 1]);
+                  __half2 h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
+                  __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]);
+                  __half2 h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
+                  pk.x = *reinterpret_cast<uint32_t*>(&h0);
+                  pk.y = *reinterpret_cast<uint32_t*>(&h1);
+                  pk.z = *reinterpret_cast<uint32_t*>(&h2);
+                  pk.w = *reinterpret_cast<uint32_t*>(&h3);
+                  *reinterpret_cast<uint4*>(o + j) = pk;
+                }
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) o[j] = __float2half_rn(f[j]);
+              }
+            } else {
+              float* o = reinterpret_cast<float*>(p.out) + size_t(bt) * p.out_batch_stride + size_t(row) * p.ldc + col0;
+              if (fullchunk) {
+  #pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                  *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
+              } else {
+                for (int j = 0; j < 32; ++j)
+                  if (col0 + j < p.N) o[j] = f[j];
+              }
+            }
+          }
+        }
+}
+
 template <int BN, bool OUT_HALF, int ACT>
 __global__ void __launch_bounds__(256, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -152,81 +233,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      const float* res_row = nullptr;
-      if (p.res != nullptr && row < p.M)
-        res_row = p.res + size_t(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr;
-#pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(t_addr + uint32_t(c * 32), v);
-        tc_wait_ld();
-        const int col0 = n0 + c * 32;
-        if (row < p.M && col0 < p.N) {
-          float f[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * oscale;
-          const bool fullchunk = (col0 + 32 <= p.N);
-          if (p.bias != nullptr) {
-            if (fullchunk) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-            }
-          }
-          if (res_row != nullptr) {
-            if (fullchunk) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4) {
-                const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);
-                f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) f[j] += res_row[col0 + j];
-            }
-          }
-          if (ACT == 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-          }
-          if (OUT_HALF) {
-            __half* o = reinterpret_cast<__half*>(p.out) + size_t(bt) * p.out_batch_stride + size_t(row) * p.ldc + col0;
-            if (fullchunk) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                uint4 pk;
-                __half2 h0 = __floats2half2_rn(f[j], f[j + 1]);
-                __half2 h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
-                __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]);
-                __half2 h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
-                pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                *reinterpret_cast<uint4*>(o + j) = pk;
-              }
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = __float2half_rn(f[j]);
-            }
-          } else {
-            float* o = reinterpret_cast<float*>(p.out) + size_t(bt) * p.out_batch_stride + size_t(row) * p.ldc + col0;
-            if (fullchunk) {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-            } else {
-              for (int j = 0; j < 32; ++j)
-                if (col0 + j < p.N) o[j] = f[j];
-            }
-          }
-        }
-      }
+      gemm_epilogue_tile<BN, OUT_HALF, ACT>(p, t_addr, row, n0, bt, oscale);
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();

@@ -227,6 +227,81 @@ sgemm_tn_kernel(const SgemmParams p) {
   }
 }
 
+// Small-M variant for the token side of the decoder (M = prompts x tokens <= ~1k rows): these GEMMs are latency-
+// not throughput-bound, so the k-slice is 64 deep (4x fewer load->sync round trips) and K can be split across
+// blockIdx.z into a workspace that splitk_reduce_kernel folds deterministically (fixed summation order).
+__global__ void __launch_bounds__(256)
+sgemm_small_kernel(const SgemmParams p, int k_per_split, float* __restrict__ ws /*[splits][M][N] or null*/) {
+  __shared__ __align__(16) float As[64][64 + 4];
+  __shared__ __align__(16) float Ws[64][64 + 4];
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  const int kbeg = blockIdx.z * k_per_split, kend = min(p.K, kbeg + k_per_split);
+  const int ty = tid / 16, tx = tid % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int k0 = kbeg; k0 < kend; k0 += 64) {
+    float4 ra[4], rw[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + 256 * i, r = f / 16, k4 = (f % 16) * 4;      // 64 rows x 16 float4
+      const int ar = m0 + r, wr = n0 + r;
+      ra[i] = (ar < p.M) ? *reinterpret_cast<const float4*>(p.A + size_t(ar) * p.lda + k0 + k4) : make_float4(0, 0, 0, 0);
+      rw[i] = (wr < p.N) ? *reinterpret_cast<const float4*>(p.W + size_t(wr) * p.ldw + k0 + k4) : make_float4(0, 0, 0, 0);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int f = tid + 256 * i, r = f / 16, k4 = (f % 16) * 4;
+      As[k4 + 0][r] = ra[i].x; As[k4 + 1][r] = ra[i].y; As[k4 + 2][r] = ra[i].z; As[k4 + 3][r] = ra[i].w;
+      Ws[k4 + 0][r] = rw[i].x; Ws[k4 + 1][r] = rw[i].y; Ws[k4 + 2][r] = rw[i].z; Ws[k4 + 3][r] = rw[i].w;
+    }
+    __syncthreads();
+#pragma unroll 16
+    for (int k = 0; k < 64; ++k) {
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 w = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (ws) { ws[(size_t(blockIdx.z) * p.M + m) * p.N + n] = v; continue; }
+      if (p.bias) v += __ldg(p.bias + n);
+      if (p.R) v += p.R[size_t(p.rmod > 0 ? m % p.rmod : m) * p.ldr + n];
+      if (p.act == 1) v = fmaxf(v, 0.f);
+      else if (p.act == 2) v = gelu_erf_f(v);
+      p.C[size_t(m) * p.ldc + n] = v;
+    }
+  }
+}
+__global__ void splitk_reduce_kernel(const SgemmParams p, const float* __restrict__ ws, int splits) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= p.M * p.N) return;
+  const int m = i / p.N, n = i % p.N;
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += ws[size_t(z) * p.M * p.N + i];
+  if (p.bias) v += __ldg(p.bias + n);
+  if (p.R) v += p.R[size_t(p.rmod > 0 ? m % p.rmod : m) * p.ldr + n];
+  if (p.act == 1) v = fmaxf(v, 0.f);
+  else if (p.act == 2) v = gelu_erf_f(v);
+  p.C[size_t(m) * p.ldc + n] = v;
+}
+
 // out[r][c] = a[r % amod][c] + b[c] (+ r-indexed table)   -- small broadcast adds used by the decoder set-up
 __global__ void add_rowvec_kernel(const float* __restrict__ a, int amod, const float* __restrict__ vec, float* __restrict__ out,
                                   int rows, int C) {
@@ -431,72 +506,96 @@ __global__ void tok_self_attn_kernel(const float* __restrict__ q, const float* _
 }
 
 // (2) token -> image cross attention: q [B][T][128]; K,V rows of `ld` floats, prompt stride kv_bstride
-//     (0 = shared by all prompts); 8 heads x 16.  One block per (prompt, head, query token): 256 threads x 16 keys,
-//     softmax over the 4096 image keys with one block-wide (max, sum, weighted-V) combine.
+//     (0 = shared by all prompts); 8 heads x 16.  One block per (prompt, head, 512-key chunk): every thread keeps its
+//     two keys' K and V rows in registers and reuses them for all T query tokens, so K/V are read exactly once.
+//     Per-chunk softmax partials (max, sum, weighted V) go to `part`; t2i_combine_kernel merges the 8 chunks.
 __global__ void __launch_bounds__(256)
 t2i_attn_kernel(const float* __restrict__ q, const float* __restrict__ K, const float* __restrict__ V, int ld,
-                size_t kv_bstride, float* __restrict__ out, int T) {
-  const int b = blockIdx.x, h = blockIdx.y, t = blockIdx.z, tid = threadIdx.x;
+                size_t kv_bstride, float* __restrict__ part /*[B][8][T][8][18]*/, int T) {
+  const int b = blockIdx.x, h = blockIdx.y, ch = blockIdx.z, tid = threadIdx.x;
   const float* Kb = K + size_t(b) * kv_bstride + h * 16;
   const float* Vb = V + size_t(b) * kv_bstride + h * 16;
   __shared__ float red[8][18];
-  float qv[16];
+  __shared__ float sq[16 * 16];
+  for (int i = tid; i < T * 16; i += 256) sq[i] = q[(size_t(b) * T + i / 16) * 128 + h * 16 + i % 16];
+  float kr[2][16], vr[2][16];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) qv[c] = q[(size_t(b) * T + t) * 128 + h * 16 + c];
-  float s[16];
-  float m = -INFINITY;
+  for (int i = 0; i < 2; ++i) {
+    const size_t key = size_t(ch) * 512 + tid + 256 * i;
+    const float4* kp = reinterpret_cast<const float4*>(Kb + key * ld);
+    const float4* vp = reinterpret_cast<const float4*>(Vb + key * ld);
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float4* kr = reinterpret_cast<const float4*>(Kb + size_t(tid + 256 * i) * ld);
-    const float4 k0 = kr[0], k1 = kr[1], k2 = kr[2], k3 = kr[3];
-    float a = qv[0] * k0.x;
-    a = fmaf(qv[1], k0.y, a); a = fmaf(qv[2], k0.z, a); a = fmaf(qv[3], k0.w, a);
-    a = fmaf(qv[4], k1.x, a); a = fmaf(qv[5], k1.y, a); a = fmaf(qv[6], k1.z, a); a = fmaf(qv[7], k1.w, a);
-    a = fmaf(qv[8], k2.x, a); a = fmaf(qv[9], k2.y, a); a = fmaf(qv[10], k2.z, a); a = fmaf(qv[11], k2.w, a);
-    a = fmaf(qv[12], k3.x, a); a = fmaf(qv[13], k3.y, a); a = fmaf(qv[14], k3.z, a); a = fmaf(qv[15], k3.w, a);
-    s[i] = a * 0.25f;                     // / sqrt(16)
-    m = fmaxf(m, s[i]);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-  if ((tid & 31) == 0) red[tid >> 5][17] = m;
-  __syncthreads();
-  m = red[0][17];
-#pragma unroll
-  for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w][17]);
-  float l = 0.f;
-  float acc[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float pexp = expf(s[i] - m);
-    l += pexp;
-    const float4* vr = reinterpret_cast<const float4*>(Vb + size_t(tid + 256 * i) * ld);
-    const float4 v0 = vr[0], v1 = vr[1], v2 = vr[2], v3 = vr[3];
-    acc[0] = fmaf(pexp, v0.x, acc[0]); acc[1] = fmaf(pexp, v0.y, acc[1]); acc[2] = fmaf(pexp, v0.z, acc[2]); acc[3] = fmaf(pexp, v0.w, acc[3]);
-    acc[4] = fmaf(pexp, v1.x, acc[4]); acc[5] = fmaf(pexp, v1.y, acc[5]); acc[6] = fmaf(pexp, v1.z, acc[6]); acc[7] = fmaf(pexp, v1.w, acc[7]);
-    acc[8] = fmaf(pexp, v2.x, acc[8]); acc[9] = fmaf(pexp, v2.y, acc[9]); acc[10] = fmaf(pexp, v2.z, acc[10]); acc[11] = fmaf(pexp, v2.w, acc[11]);
-    acc[12] = fmaf(pexp, v3.x, acc[12]); acc[13] = fmaf(pexp, v3.y, acc[13]); acc[14] = fmaf(pexp, v3.z, acc[14]); acc[15] = fmaf(pexp, v3.w, acc[15]);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    l += __shfl_xor_sync(0xffffffffu, l, o);
-#pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-  }
-  if ((tid & 31) == 0) {
-    red[tid >> 5][16] = l;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) red[tid >> 5][c] = acc[c];
+    for (int j = 0; j < 4; ++j) {
+      const float4 a = kp[j], c = vp[j];
+      kr[i][4 * j] = a.x; kr[i][4 * j + 1] = a.y; kr[i][4 * j + 2] = a.z; kr[i][4 * j + 3] = a.w;
+      vr[i][4 * j] = c.x; vr[i][4 * j + 1] = c.y; vr[i][4 * j + 2] = c.z; vr[i][4 * j + 3] = c.w;
+    }
   }
   __syncthreads();
-  if (tid < 16) {
-    float num = 0.f, den = 0.f;
+  for (int t = 0; t < T; ++t) {
+    float s0 = 0.f, s1 = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) { num += red[w][tid]; den += red[w][16]; }
-    out[(size_t(b) * T + t) * 128 + h * 16 + tid] = num / den;
+    for (int c = 0; c < 16; ++c) {
+      const float qc = sq[t * 16 + c];
+      s0 = fmaf(qc, kr[0][c], s0);
+      s1 = fmaf(qc, kr[1][c], s1);
+    }
+    s0 *= 0.25f;                          // / sqrt(16)
+    s1 *= 0.25f;
+    float m = fmaxf(s0, s1);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((tid & 31) == 0) red[tid >> 5][17] = m;
+    __syncthreads();
+    m = red[0][17];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w][17]);
+    const float p0 = expf(s0 - m), p1 = expf(s1 - m);
+    float l = p0 + p1;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = fmaf(p0, vr[0][c], p1 * vr[1][c]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      l += __shfl_xor_sync(0xffffffffu, l, o);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+    }
+    __syncthreads();                       // everyone has read red[][17]
+    if ((tid & 31) == 0) {
+      red[tid >> 5][16] = l;
+#pragma unroll
+      for (int c = 0; c < 16; ++c) red[tid >> 5][c] = acc[c];
+    }
+    __syncthreads();
+    if (tid < 18) {
+      float v = 0.f;
+      if (tid == 17) v = m;
+      else
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][tid];
+      part[((((size_t(b) * 8 + h) * T + t) * 8) + ch) * 18 + tid] = v;
+    }
+    __syncthreads();
   }
+}
+// merge the 8 key-chunk partials: out[b][t][h*16 + c] = sum_i acc_i e^(m_i - M) / sum_i l_i e^(m_i - M)
+__global__ void t2i_combine_kernel(const float* __restrict__ part, float* __restrict__ out /*[B][T][128]*/, int B, int T) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (b, h, t, c)
+  if (i >= B * 8 * T * 16) return;
+  const int c = i % 16, t = (i / 16) % T, h = (i / (16 * T)) % 8, b = i / (16 * T * 8);
+  const float* p = part + (((size_t(b) * 8 + h) * T + t) * 8) * 18;
+  float M = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) M = fmaxf(M, p[k * 18 + 17]);
+  float num = 0.f, den = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const float w = expf(p[k * 18 + 17] - M);
+    num = fmaf(p[k * 18 + c], w, num);
+    den = fmaf(p[k * 18 + 16], w, den);
+  }
+  out[(size_t(b) * T + t) * 128 + h * 16 + c] = num / den;
 }
 
 // split an fp32 value into fp16 hi + lo (hi + lo == v to ~2^-22 relative): operands of the 3-term tensor-core GEMM
@@ -506,9 +605,10 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 }
 
 // (3) image -> token cross attention: Q rows of `ldq` floats, prompt stride q_bstride (0 = shared); k,v [B][T][128];
-//     one thread per (prompt, image token, head); k,v of the prompt staged in smem.  The result feeds the out_proj
-//     tensor-core GEMM, so it is written directly as the split-fp16 operand [B*4096][hi(128) | lo(128) | hi(128)].
-__global__ void __launch_bounds__(256)
+//     one thread per (prompt, image token) looping over the 8 heads, so the prompt's k,v in smem are read as warp-wide
+//     broadcasts.  The result feeds the out_proj tensor-core GEMM and is written directly as the split-fp16 operand
+//     [B*4096][hi(128) | lo(128) | hi(128)].
+__global__ void __launch_bounds__(128)
 i2t_attn_kernel(const float* __restrict__ Q, int ldq, size_t q_bstride, const float* __restrict__ k, const float* __restrict__ v,
                 __half* __restrict__ out_split /*[B][4096][384]*/, int T) {
   extern __shared__ float sm[];
@@ -520,43 +620,59 @@ i2t_attn_kernel(const float* __restrict__ Q, int ldq, size_t q_bstride, const fl
     sv[i] = v[size_t(b) * T * 128 + i];
   }
   __syncthreads();
-  const int idx = blockIdx.x * blockDim.x + threadIdx.x;      // (token, head)
-  if (idx >= 4096 * 8) return;
-  const int token = idx >> 3, h = idx & 7;
-  const float4* qr = reinterpret_cast<const float4*>(Q + size_t(b) * q_bstride + size_t(token) * ldq + h * 16);
-  const float4 q0 = qr[0], q1 = qr[1], q2 = qr[2], q3 = qr[3];
-  const float qv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-  float m = -INFINITY;
-  for (int t = 0; t < T; ++t) {
-    float a = 0.f;
+  const int token = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* qrow = Q + size_t(b) * q_bstride + size_t(token) * ldq;
+  __half* orow = out_split + (size_t(b) * 4096 + token) * 384;
+#pragma unroll 1
+  for (int h = 0; h < 8; ++h) {
+    const float4* qr = reinterpret_cast<const float4*>(qrow + h * 16);
+    const float4 q0 = qr[0], q1 = qr[1], q2 = qr[2], q3 = qr[3];
+    const float qv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+    float m = -INFINITY;
+    for (int t = 0; t < T; ++t) {
+      const float4* kk = reinterpret_cast<const float4*>(sk + t * 128 + h * 16);
+      float a = 0.f;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) a = fmaf(qv[c], sk[t * 128 + h * 16 + c], a);
-    m = fmaxf(m, a * 0.25f);
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = kk[j];
+        a = fmaf(qv[4 * j], w.x, a); a = fmaf(qv[4 * j + 1], w.y, a); a = fmaf(qv[4 * j + 2], w.z, a); a = fmaf(qv[4 * j + 3], w.w, a);
+      }
+      m = fmaxf(m, a * 0.25f);
+    }
+    float l = 0.f;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float4* kk = reinterpret_cast<const float4*>(sk + t * 128 + h * 16);
+      const float4* vv = reinterpret_cast<const float4*>(sv + t * 128 + h * 16);
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = kk[j];
+        a = fmaf(qv[4 * j], w.x, a); a = fmaf(qv[4 * j + 1], w.y, a); a = fmaf(qv[4 * j + 2], w.z, a); a = fmaf(qv[4 * j + 3], w.w, a);
+      }
+      const float pexp = expf(a * 0.25f - m);
+      l += pexp;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = vv[j];
+        acc[4 * j] = fmaf(pexp, w.x, acc[4 * j]); acc[4 * j + 1] = fmaf(pexp, w.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(pexp, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(pexp, w.w, acc[4 * j + 3]);
+      }
+    }
+    const float inv = 1.0f / l;
+    __half hi[16], lo[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) split_f16(acc[c] * inv, hi[c], lo[c]);
+    __half* o = orow + h * 16;
+    reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(hi)[0];
+    reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(hi)[1];
+    reinterpret_cast<uint4*>(o + 128)[0] = reinterpret_cast<uint4*>(lo)[0];
+    reinterpret_cast<uint4*>(o + 128)[1] = reinterpret_cast<uint4*>(lo)[1];
+    reinterpret_cast<uint4*>(o + 256)[0] = reinterpret_cast<uint4*>(hi)[0];
+    reinterpret_cast<uint4*>(o + 256)[1] = reinterpret_cast<uint4*>(hi)[1];
   }
-  float l = 0.f;
-  float acc[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-  for (int t = 0; t < T; ++t) {
-    float a = 0.f;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) a = fmaf(qv[c], sk[t * 128 + h * 16 + c], a);
-    const float pexp = expf(a * 0.25f - m);
-    l += pexp;
-#pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = fmaf(pexp, sv[t * 128 + h * 16 + c], acc[c]);
-  }
-  const float inv = 1.0f / l;
-  __half hi[16], lo[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) split_f16(acc[c] * inv, hi[c], lo[c]);
-  __half* o = out_split + (size_t(b) * 4096 + token) * 384 + h * 16;
-  reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(hi)[0];
-  reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(hi)[1];
-  reinterpret_cast<uint4*>(o + 128)[0] = reinterpret_cast<uint4*>(lo)[0];
-  reinterpret_cast<uint4*>(o + 128)[1] = reinterpret_cast<uint4*>(lo)[1];
-  reinterpret_cast<uint4*>(o + 256)[0] = reinterpret_cast<uint4*>(hi)[0];
-  reinterpret_cast<uint4*>(o + 256)[1] = reinterpret_cast<uint4*>(hi)[1];
 }
 
 // LayerNorm over 256 channels (decoder norm4, eps 1e-5) writing the fp32 result (optional) and its split-fp16

@@ -29,6 +29,9 @@ def _rand(shape, seed, scale=1.0, dtype=torch.float16):
     (128, 128, 64, 128), (128, 256, 128, 256), (256, 160, 192, 160),
     (4096, 3840, 1280, 0), (4096, 1280, 5120, 0), (4096, 5120, 1280, 0),
     (4096, 384, 128, 0), (200, 136, 160, 0), (4096, 480, 160, 0), (4096, 256, 2304, 0),
+    # CTA-pair (cta_group::2) kernel: force_bn = 1000 + N tile
+    (256, 256, 64, 1256), (512, 256, 256, 1128), (4096, 3840, 1280, 1256), (4096, 1280, 5120, 1160),
+    (4096, 1280, 1280, 1128), (700, 520, 200, 1256), (131072, 384, 768, 0),
 ])
 def test_gemm_fp32_out_bias_residual(eng64, M, N, K, bn):
     A, B = _rand((M, K), 1), _rand((N, K), 2, 1.0 / math.sqrt(K))
