@@ -206,22 +206,32 @@ def run_ours(args):
     import samrs_b200
     from samrs_b200.engine import Engine
     g = geometry(VARIANT)
-    eng = Engine(VARIANT, device)
+    # NS tiles in flight per GPU: each has its own engine (activations + weight copy) and CUDA stream, so one tile's
+    # kernel tails / launch gaps are filled by the other tile's kernels (tiles are independent)
+    NS = max(1, int(os.environ.get("SAMRS_STREAMS", "2")))
     if world > 1:
         sd = broadcast_state_dict(g, rank, world, device)
     else:
         sd = synthetic_state_dict(VARIANT, 0)
-    eng.load_state_dict(sd)
+    engines = []
+    for _ in range(NS):
+        e_ = Engine(VARIANT, device)
+        e_.load_state_dict(sd)
+        engines.append(e_)
+    eng = engines[0]
     del sd
     torch.cuda.empty_cache()
+    streams = [torch.cuda.Stream(device=device) for _ in range(NS)]
 
-    # the drop-in predictor shares the engine (same weights, no second copy)
+    # the drop-in predictors share the engines (same weights, no further copies)
     sys.path.insert(0, samrs_b200.DROPIN_PATH)
     from segment_anything import SamPredictor
     from segment_anything.modeling import Sam
-    sam = Sam(g)
-    sam.engine, sam._device = eng, eng.device
-    predictor = SamPredictor(sam)
+    predictors = []
+    for e_ in engines:
+        sam = Sam(g)
+        sam.engine, sam._device = e_, e_.device
+        predictors.append(SamPredictor(sam))
 
     # this rank's tiles: rank r takes tiles r, r+world, ... (files[rank::world])
     idxs = [rank + world * i for i in range(N_TILES)]
@@ -231,30 +241,34 @@ def run_ours(args):
     tiles_d = [t.to(device) for t in tiles_h]
     boxes_d = [b.to(device) for b in boxes_h]
     labels_d = [l.to(device) for l in labels_h]
-    canvas = torch.empty((1024, 1024), dtype=torch.uint8, device=device)
-    out_h = torch.empty((1024, 1024), dtype=torch.uint8).pin_memory()
+    canvases = [torch.empty((1024, 1024), dtype=torch.uint8, device=device) for _ in range(NS)]
+    outs_h = [torch.empty((1024, 1024), dtype=torch.uint8).pin_memory() for _ in range(NS)]
 
     def step_resident(i):
-        j = i % N_TILES
-        eng.encode(tiles_d[j])
-        low, _ = eng.decode(boxes=boxes_d[j], multimask_output=False)
-        eng.postprocess(low, (1024, 1024), (1024, 1024))
-        canvas.fill_(255)
-        eng.semantic_reduce(low, labels_d[j], canvas)
+        j, k = i % N_TILES, i % NS
+        en, canvas = engines[k], canvases[k]
+        with torch.cuda.stream(streams[k]):
+            en.encode(tiles_d[j])
+            low, _ = en.decode(boxes=boxes_d[j], multimask_output=False)
+            en.postprocess(low, (1024, 1024), (1024, 1024))
+            canvas.fill_(255)
+            en.semantic_reduce(low, labels_d[j], canvas)
 
     def step_e2e(i):
-        j = i % N_TILES
-        img = tiles_h[j].numpy()                                    # host HWC uint8 (pinned)
-        predictor.set_image(img)                                     # H2D 3 MiB + encoder
-        bx = boxes_h[j].to(device, non_blocking=True)                # H2D 512 B
-        lb = labels_h[j].to(device, non_blocking=True)
-        canvas.fill_(255)
-        for s in range(0, BOXES, CHUNK):                             # the driver's 20 + 12 chunks
-            tb = predictor.transform.apply_boxes_torch(bx[s:s + CHUNK], img.shape[:2])
-            _, _, low = predictor.predict_torch(None, None, boxes=tb, mask_input=None, multimask_output=False)
-            eng.semantic_reduce(low, lb[s:s + CHUNK], canvas)
-        out_h.copy_(canvas, non_blocking=True)                       # D2H 1 MiB label map
-        torch.cuda.current_stream().synchronize()                    # the host consumes the result every step
+        j, k = i % N_TILES, i % NS
+        en, canvas, predictor = engines[k], canvases[k], predictors[k]
+        with torch.cuda.stream(streams[k]):
+            streams[k].synchronize()                                     # the host consumed this slot's previous result
+            img = tiles_h[j].numpy()                                    # host HWC uint8 (pinned)
+            predictor.set_image(img)                                     # H2D 3 MiB + encoder
+            bx = boxes_h[j].to(device, non_blocking=True)                # H2D 512 B
+            lb = labels_h[j].to(device, non_blocking=True)
+            canvas.fill_(255)
+            for s in range(0, BOXES, CHUNK):                             # the driver's 20 + 12 chunks
+                tb = predictor.transform.apply_boxes_torch(bx[s:s + CHUNK], img.shape[:2])
+                _, _, low = predictor.predict_torch(None, None, boxes=tb, mask_input=None, multimask_output=False)
+                en.semantic_reduce(low, lb[s:s + CHUNK], canvas)
+            outs_h[k].copy_(canvas, non_blocking=True)                   # D2H 1 MiB label map
 
     def barrier():
         if world > 1:
@@ -264,17 +278,29 @@ def run_ours(args):
     def timed(fn, steps, profile=False):
         barrier()
         if profile:
-            eng.profile_begin()
-        l0 = eng.launch_count()
+            for e_ in engines:
+                e_.profile_begin()
+        l0 = sum(e_.launch_count() for e_ in engines)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
+        cur = torch.cuda.current_stream()
+        a.record(cur)
+        for st_ in streams:
+            st_.wait_stream(cur)
         for i in range(steps):
             fn(i)
-        b.record()
+        for st_ in streams:
+            cur.wait_stream(st_)
+        b.record(cur)
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
-        prof = eng.profile_end() if profile else None
-        launches = eng.launch_count() - l0
+        prof = None
+        if profile:
+            prof = {}
+            for e_ in engines:
+                for k_, (ms_, n_) in e_.profile_end().items():
+                    o = prof.get(k_, (0.0, 0))
+                    prof[k_] = (o[0] + ms_, o[1] + n_)
+        launches = sum(e_.launch_count() for e_ in engines) - l0
         if world > 1:
             t = torch.tensor([ms], device=device)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -309,7 +335,7 @@ def run_ours(args):
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 tensor-core operands, f32 accumulate / residual / softmax / decoder", "data": "synthetic",
         "config": {"workload": "SAM ViT-H, 1024x1024 synthetic RS tile, 32 hbox prompts per tile (BASELINE.json configs[1])",
-                   "tiles_per_rank_cycled": N_TILES, "l2": "working set (1.3 GB fp16 weights) exceeds the 126 MB L2",
+                   "tiles_per_rank_cycled": N_TILES, "tiles_in_flight_per_gpu": NS, "l2": "working set (1.3 GB fp16 weights) exceeds the 126 MB L2",
                    "parallelism": f"tile-sharded dp{world}, weights broadcast once over NCCL" if world > 1 else "single GPU",
                    "step": "encode + decode(32) + bool masks + fused label map"},
         "gpu_launches": launches,

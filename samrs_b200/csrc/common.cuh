@@ -77,6 +77,17 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uin
       : "memory");
 }
 
+// TMA store of a shared-memory box to global memory (bulk async group); rows / columns beyond the tensor are clipped
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -226,5 +237,8 @@ int make_tmap_2d(CUtensorMap* out, const void* base, uint64_t inner, uint64_t ou
                  uint32_t box_inner, uint32_t box_outer);
 int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t pitch1_bytes,
                  uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
+// output tensor map for the GEMM epilogue's TMA stores: [batch][M][N] fp16 (no swizzle) or fp32 (128-byte swizzle), box 32x32
+int make_tmap_out(CUtensorMap* out, const void* base, bool half, uint64_t N, uint64_t M, uint64_t batch, uint64_t ld_elems,
+                  uint64_t batch_stride_elems);
 
 }  // namespace samrs

@@ -76,6 +76,22 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
   return 0;
 }
 
+int make_tmap_out(CUtensorMap* out, const void* base, bool half, uint64_t N, uint64_t M, uint64_t batch, uint64_t ld_elems,
+                  uint64_t batch_stride_elems) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) SAMRS_FAIL("cuTensorMapEncodeTiled unavailable");
+  const uint64_t es = half ? 2 : 4;
+  cuuint64_t dims[3] = {N, M, batch};
+  cuuint64_t strides[2] = {ld_elems * es, (batch > 1 ? batch_stride_elems : ld_elems * M) * es};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = enc(out, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, half ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) SAMRS_FAIL("cuTensorMapEncodeTiled(out) failed");
+  return 0;
+}
+
 // ------------------------------------------------------------------ GEMM launcher
 static int64_t* g_launch_counter = nullptr;   // points into the active engine
 static inline void count_launch(int n = 1) {
@@ -83,28 +99,28 @@ static inline void count_launch(int n = 1) {
 }
 
 template <int BN, bool OH, int ACT>
-static int launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, int grid, cudaStream_t st) {
+static int launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
     SAMRS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OH, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  gemm_tc_kernel<BN, OH, ACT><<<grid, 256, Cfg::kSmemBytes, st>>>(tA, tB, p);
+  gemm_tc_kernel<BN, OH, ACT><<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(tA, tB, tC, p);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
 }
 
 template <int BN, bool OH, int ACT>
-static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const GemmParams& p, int grid, cudaStream_t st) {
+static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   static bool attr_done = false;
   if (!attr_done) {
     SAMRS_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<BN, OH, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     attr_done = true;
   }
-  gemm_tc2_kernel<BN, OH, ACT><<<grid, 256, Cfg::kSmemBytes, st>>>(tA, tB, p);
+  gemm_tc2_kernel<BN, OH, ACT><<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(tA, tB, tC, p);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -128,12 +144,12 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   bool pair = force_bn >= 1000;
   if (force_bn == 0) {
     // pick the (kernel, N tile) with the smallest modelled duration = waves x per-tile time
-    const int cands[3] = {256, 160, 128};
+    const int cands[4] = {256, 224, 160, 128};
     double best = 1e30;
     for (int pr = 0; pr < 2; ++pr) {
       static const bool no_pair = getenv("SAMRS_NO_PAIR") != nullptr;
       if (pr == 1 && (no_pair || p.batch != 1 || a_map_rank3 || p.M < 256 || (num_sms & 1))) continue;
-      for (int i = 0; i < 3; ++i) {
+      for (int i = 0; i < 4; ++i) {
         const int c = cands[i];
         const long tm = (p.M + (pr ? 255 : 127)) / (pr ? 256 : 128), tn = (p.N + c - 1) / c;
         const long units = pr ? num_sms / 2 : num_sms;
@@ -149,18 +165,22 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   if (a_map_rank3) tA = *a_map_rank3;
   else SAMRS_TRY(make_tmap_2d(&tA, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, GEMM_BK, GEMM_BM));
   SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t(pair ? bn / 2 : bn)));
+  CUtensorMap tC;
+  SAMRS_TRY(make_tmap_out(&tC, p.out, out_half, uint64_t(p.N), uint64_t(p.M), uint64_t(p.batch), uint64_t(p.ldc), uint64_t(p.out_batch_stride)));
+  if (p.res != nullptr && (p.ldr % 4 != 0)) SAMRS_FAIL("gemm: residual leading dimension must be a multiple of 4");
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   if (pair) {
     const int pairs = num_sms / 2;
     const int grid2 = 2 * (tiles < pairs ? tiles : pairs);
 #define SAMRS_GEMM2_CASE(BN_)                                                                       \
   if (bn == BN_) {                                                                                  \
-    if (out_half && act == 0) return launch_gemm2_inst<BN_, true, 0>(tA, tB, p, grid2, stream);     \
-    if (out_half && act == 1) return launch_gemm2_inst<BN_, true, 1>(tA, tB, p, grid2, stream);     \
-    if (!out_half && act == 0) return launch_gemm2_inst<BN_, false, 0>(tA, tB, p, grid2, stream);   \
+    if (out_half && act == 0) return launch_gemm2_inst<BN_, true, 0>(tA, tB, tC, p, grid2, stream);     \
+    if (out_half && act == 1) return launch_gemm2_inst<BN_, true, 1>(tA, tB, tC, p, grid2, stream);     \
+    if (!out_half && act == 0) return launch_gemm2_inst<BN_, false, 0>(tA, tB, tC, p, grid2, stream);   \
     SAMRS_FAIL("gemm: unsupported epilogue");                                                       \
   }
     SAMRS_GEMM2_CASE(256)
+    SAMRS_GEMM2_CASE(224)
     SAMRS_GEMM2_CASE(160)
     SAMRS_GEMM2_CASE(128)
 #undef SAMRS_GEMM2_CASE
@@ -169,12 +189,13 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   const int grid = tiles < num_sms ? tiles : num_sms;
 #define SAMRS_GEMM_CASE(BN_)                                                                        \
   if (bn == BN_) {                                                                                  \
-    if (out_half && act == 0) return launch_gemm_inst<BN_, true, 0>(tA, tB, p, grid, stream);       \
-    if (out_half && act == 1) return launch_gemm_inst<BN_, true, 1>(tA, tB, p, grid, stream);       \
-    if (!out_half && act == 0) return launch_gemm_inst<BN_, false, 0>(tA, tB, p, grid, stream);     \
+    if (out_half && act == 0) return launch_gemm_inst<BN_, true, 0>(tA, tB, tC, p, grid, stream);       \
+    if (out_half && act == 1) return launch_gemm_inst<BN_, true, 1>(tA, tB, tC, p, grid, stream);       \
+    if (!out_half && act == 0) return launch_gemm_inst<BN_, false, 0>(tA, tB, tC, p, grid, stream);     \
     SAMRS_FAIL("gemm: unsupported epilogue");                                                       \
   }
   SAMRS_GEMM_CASE(256)
+  SAMRS_GEMM_CASE(224)
   SAMRS_GEMM_CASE(160)
   SAMRS_GEMM_CASE(128)
 #undef SAMRS_GEMM_CASE
@@ -255,7 +276,7 @@ struct Engine {
 
   // encoder activations
   __half *a_pe, *xn, *qkv, *attn_o, *hid, *x16, *neck_ln16, *neck_col;
-  float *x, *rel, *neck0, *neck2, *feat_tok, *feat_nchw;
+  float *x, *delta, *rel, *neck0, *neck2, *feat_tok, *feat_nchw;
   // per-image decoder cache
   float *src0, *K0, *V0, *Qi0;
   float* pp_full = nullptr;            // postprocess scratch for non-1024 sizes
@@ -317,15 +338,15 @@ static int sgemm(cudaStream_t st, const float* A, int lda, const float* W, int l
 
 template <typename OutT, int ACT>
 static int ln_rows(cudaStream_t st, const float* in, int ld_in, const float* g, const float* b, float eps, OutT* out, int ld_out,
-                   int rows, int C) {
+                   int rows, int C, const float* add = nullptr, float* x_out = nullptr) {
   const int nv = C / 4;
   const int threads = 256, rows_per_block = threads / 32;
   const int grid = (rows + rows_per_block - 1) / rows_per_block;
   if (C % 4 != 0) SAMRS_FAIL("layernorm: C must be a multiple of 4");
-  if (nv <= 32) ln_rows_kernel<OutT, ACT, 1><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
-  else if (nv <= 64) ln_rows_kernel<OutT, ACT, 2><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
-  else if (nv <= 192) ln_rows_kernel<OutT, ACT, 6><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
-  else if (nv <= 320) ln_rows_kernel<OutT, ACT, 10><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
+  if (nv <= 32) ln_rows_kernel<OutT, ACT, 1><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C, add, x_out);
+  else if (nv <= 64) ln_rows_kernel<OutT, ACT, 2><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C, add, x_out);
+  else if (nv <= 192) ln_rows_kernel<OutT, ACT, 6><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C, add, x_out);
+  else if (nv <= 320) ln_rows_kernel<OutT, ACT, 10><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C, add, x_out);
   else SAMRS_FAIL("layernorm: C too large");
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -361,7 +382,7 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
     SAMRS_TRY(make_tmap_3d(&tA, qkv, uint64_t(hd), uint64_t(e->heads), 4096, uint64_t(hd) * 2, uint64_t(3 * D) * 2, GEMM_BK, 1, GEMM_BM));
     GemmParams gp;
     gp.M = 4096; gp.N = NP; gp.K = hd; gp.out = e->rel; gp.ldc = NP; gp.bias = nullptr; gp.res = nullptr; gp.ldr = 0; gp.res_mod = 0;
-    gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f;
+    gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f; gp.dbg = nullptr;
     SAMRS_TRY(launch_gemm_tc(nullptr, 8, reltab, hd, gp, false, 0, e->num_sms, st, global ? 256 : 128, &tA));
   }
   ProfScope ps2(global ? PC_ATTN_GLOB : PC_ATTN_WIN, st);
@@ -637,6 +658,7 @@ static int alloc_activations(Engine* e) {
   const size_t D = e->D, T = 4096;
   SAMRS_TRY(e->alloc(&e->a_pe, T * 768));
   SAMRS_TRY(e->alloc(&e->x, T * D));
+  SAMRS_TRY(e->alloc(&e->delta, T * D));
   SAMRS_TRY(e->alloc(&e->xn, T * D));
   SAMRS_TRY(e->alloc(&e->qkv, T * 3 * D));
   SAMRS_TRY(e->alloc(&e->rel, size_t(e->heads) * T * 256));
@@ -710,7 +732,7 @@ static int gemm_enc(Engine* e, cudaStream_t st, const __half* A, int lda, const 
   p.out = out; p.ldc = ldc;
   p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.tiles_m = p.tiles_n = 0;
-  p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f;
+  p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f; p.dbg = nullptr;
   ProfScope ps(PC_GEMM, st);
   return launch_gemm_tc(A, lda, W, K, p, out_half, act, e->num_sms, st, 0);
 }
@@ -739,16 +761,17 @@ static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, flo
   SAMRS_TRY(gemm_enc(e, st, e->a_pe, 768, e->w_patch, T, D, 768, e->x, D, false, e->b_patch, e->pos_embed, D, 0, 0));
   for (int i = 0; i < e->depth; ++i) {
     const BlockWeights& b = e->blocks[i];
-    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln1w, b.ln1b, 1e-6f, e->xn, D, T, D))); }
+    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln1w, b.ln1b, 1e-6f, e->xn, D, T, D, i > 0 ? e->delta : nullptr, e->x))); }
     SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.wqkv, T, 3 * D, D, e->qkv, 3 * D, true, b.bqkv_eff, nullptr, 0, 0, 0));
     SAMRS_TRY(encoder_attention(e, st, e->qkv, b.reltab, b.global, e->attn_o));
-    SAMRS_TRY(gemm_enc(e, st, e->attn_o, D, b.wproj, T, D, D, e->x, D, false, b.bproj_eff, e->x, D, 0, 0));
-    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln2w, b.ln2b, 1e-6f, e->xn, D, T, D))); }
+    // proj / lin2 write their fp32 output (bias included) to `delta`; the following LayerNorm applies x += delta
+    SAMRS_TRY(gemm_enc(e, st, e->attn_o, D, b.wproj, T, D, D, e->delta, D, false, b.bproj_eff, nullptr, 0, 0, 0));
+    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln2w, b.ln2b, 1e-6f, e->xn, D, T, D, e->delta, e->x))); }
     SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.w1, T, 4 * D, D, e->hid, 4 * D, true, b.b1, nullptr, 0, 0, 1));
-    SAMRS_TRY(gemm_enc(e, st, e->hid, 4 * D, b.w2, T, D, 4 * D, e->x, D, false, b.b2, e->x, D, 0, 0));
+    SAMRS_TRY(gemm_enc(e, st, e->hid, 4 * D, b.w2, T, D, 4 * D, e->delta, D, false, b.b2, nullptr, 0, 0, 0));
   }
   // neck (image_encoder.py:88-104)
-  cast_f32_f16_kernel<<<unsigned((size_t(T) * D / 4 + 255) / 256), 256, 0, st>>>(e->x, e->x16, size_t(T) * D / 4);
+  cast_f32_f16_kernel<<<unsigned((size_t(T) * D / 4 + 255) / 256), 256, 0, st>>>(e->x, e->x16, size_t(T) * D / 4, e->delta);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   SAMRS_TRY(gemm_enc(e, st, e->x16, D, e->w_neck0, T, 256, D, e->neck0, 256, false, nullptr, nullptr, 0, 0, 0));
@@ -771,7 +794,7 @@ static int gemm_dec(Engine* e, cudaStream_t st, const __half* A3, const __half* 
                     const float* bias, const float* res, int ldr, int res_mod) {
   GemmParams p;
   p.M = M; p.N = N; p.K = K3; p.out = out; p.ldc = ldc; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
-  p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f;
+  p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f; p.dbg = nullptr;
   return launch_gemm_tc(A3, K3, W3, K3, p, false, 0, e->num_sms, st, 0);
 }
 
@@ -940,6 +963,8 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
 
 // ====================================================================== C ABI
 using namespace samrs;
+static void* g_gemm_dbg = nullptr;      // device buffer of 4096 u64 for gemm pipeline traces (tests/tools only)
+extern "C" void samrs_test_set_gemm_trace(void* dev_buf) { g_gemm_dbg = dev_buf; }
 
 struct LaunchScope {
   explicit LaunchScope(Engine* e) {
@@ -1138,6 +1163,7 @@ int samrs_test_gemm(void* engine, const void* A, const void* B, int M, int N, in
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldc = N; p.bias = bias; p.res = res; p.ldr = N; p.res_mod = 0; p.tiles_m = p.tiles_n = 0;
   p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f;
+  p.dbg = static_cast<unsigned long long*>(g_gemm_dbg);
   return set_err(e, launch_gemm_tc(static_cast<const __half*>(A), K, static_cast<const __half*>(B), K, p, out_half != 0, act_gelu, e->num_sms,
                                    static_cast<cudaStream_t>(stream), force_bn));
 }

@@ -29,110 +29,125 @@ struct GemmParams {
   int a_rank3;
   long long out_batch_stride;   // elements between consecutive batch outputs
   float out_scale;      // accumulator is multiplied by this before bias/residual (split-weight scaling); 0 -> 1
+  unsigned long long* dbg;   // optional: CTA 0 records clock64() at pipeline events (tools/gemm_trace.py)
 };
+__device__ __forceinline__ void gemm_dbg(const GemmParams& p, int slot) {
+  if (p.dbg != nullptr && blockIdx.x == 0 && slot < 4096) p.dbg[slot] = clock64();
+}
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // one 128-byte swizzle atom of fp16
+constexpr int GEMM_EPI_WARPS = 8;                    // warps 4..11: two column groups of four (TMEM lane quadrant = warp % 4)
+constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
+constexpr int GEMM_EPI_SMEM = GEMM_EPI_WARPS * 4096;       // one 32x32 fp32 staging block per epilogue warp
 
 template <int BN>
 struct GemmCfg {
   static constexpr int kStageBytes = GEMM_BM * 128 + BN * 128;
-  static constexpr int kStages = (BN >= 256) ? 4 : (BN >= 160 ? 5 : 6);
+  // as many stages as fit: bytes in flight per SM, not tile shape, set the achievable L2->SM feed rate
+  static constexpr int kStages = (226 * 1024 - 1280 - GEMM_EPI_SMEM) / kStageBytes > 8 ? 8 : (226 * 1024 - 1280 - GEMM_EPI_SMEM) / kStageBytes;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + GEMM_EPI_SMEM;
 };
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// Epilogue of one accumulator tile for the thread that owns TMEM lane (row): BN fp32 columns -> scale, bias,
-// residual, activation -> fp16 / fp32 global stores (each thread writes contiguous 64- or 128-byte runs of its row).
+
+// Epilogue of one accumulator tile, executed by one warp for its 32 TMEM lanes (rows row0 .. row0+31), 32 columns at
+// a time: tcgen05.ld -> scale + bias (+ residual) + activation in registers -> the warp's 32x32 block is staged in
+// shared memory and written out by ONE asynchronous TMA store (rows / columns beyond M / N are clipped by the TMA
+// unit).  The pipeline trace in profiles/r01_gemm_trace.txt shows why: while the TMA producer saturates the L2, every
+// ld.global / st.global issued by the epilogue warps takes 0.5-6 k cycles, which made the first two epilogue versions
+// (row-per-thread stores, then staged coalesced stores) as long as the main loop itself.  Here the only global loads
+// left are the bias (prefetched before the accumulator is ready) and the optional residual (prefetched one chunk
+// ahead), and the stores never stall the warp.
 template <int BN, bool OUT_HALF, int ACT>
-__device__ __forceinline__ void gemm_epilogue_tile(const GemmParams& p, uint32_t t_addr, int row, int n0, int bt, float oscale) {
-      const float* res_row = nullptr;
-        if (p.res != nullptr && row < p.M)
-          res_row = p.res + size_t(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr;
-  #pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld32(t_addr + uint32_t(c * 32), v);
-          tc_wait_ld();
-          const int col0 = n0 + c * 32;
-          if (row < p.M && col0 < p.N) {
-            float f[32];
-  #pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]) * oscale;
-            const bool fullchunk = (col0 + 32 <= p.N);
-            if (p.bias != nullptr) {
-              if (fullchunk) {
-  #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0 + j));
-                  f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) f[j] += __ldg(p.bias + col0 + j);
-              }
-            }
-            if (res_row != nullptr) {
-              if (fullchunk) {
-  #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                  const float4 r = *reinterpret_cast<const float4*>(res_row + col0 + j);
-                  f[j] += r.x; f[j + 1] += r.y; f[j + 2] += r.z; f[j + 3] += r.w;
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) f[j] += res_row[col0 + j];
-              }
-            }
-            if (ACT == 1) {
-  #pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
-            }
-            if (OUT_HALF) {
-              __half* o = reinterpret_cast<__half*>(p.out) + size_t(bt) * p.out_batch_stride + size_t(row) * p.ldc + col0;
-              if (fullchunk) {
-  #pragma unroll
-                for (int j = 0; j < 32; j += 8) {
-                  uint4 pk;
-                  __half2 h0 = __floats2half2_rn(f[j], f[j + 1]);
-                  __half2 h1 = __floats2half2_rn(f[j + 2], f[j + 3]);
-                  __half2 h2 = __floats2half2_rn(f[j + 4], f[j + 5]);
-                  __half2 h3 = __floats2half2_rn(f[j + 6], f[j + 7]);
-                  pk.x = *reinterpret_cast<uint32_t*>(&h0);
-                  pk.y = *reinterpret_cast<uint32_t*>(&h1);
-                  pk.z = *reinterpret_cast<uint32_t*>(&h2);
-                  pk.w = *reinterpret_cast<uint32_t*>(&h3);
-                  *reinterpret_cast<uint4*>(o + j) = pk;
-                }
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) o[j] = __float2half_rn(f[j]);
-              }
-            } else {
-              float* o = reinterpret_cast<float*>(p.out) + size_t(bt) * p.out_batch_stride + size_t(row) * p.ldc + col0;
-              if (fullchunk) {
-  #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                  *reinterpret_cast<float4*>(o + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              } else {
-                for (int j = 0; j < 32; ++j)
-                  if (col0 + j < p.N) o[j] = f[j];
-              }
-            }
-          }
-        }
+__device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CUtensorMap* tmC, uint32_t t_addr, int row0, int n0,
+                                                   int bt, float oscale, uint8_t* stage /*4 KiB, 1024-B aligned*/, int lane,
+                                                   const float (&bias_r)[BN / 32], int chunk_begin, int chunk_end) {
+  constexpr int NCH = BN / 32;
+  const int row = row0 + lane;
+  const float* res_row = nullptr;
+  if (p.res != nullptr && row < p.M) res_row = p.res + size_t(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr + n0;
+  float4 rn[8];
+  auto load_res = [&](int c) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      rn[j] = (res_row != nullptr && n0 + c * 32 + 4 * j < p.N) ? *reinterpret_cast<const float4*>(res_row + c * 32 + 4 * j)
+                                                                : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  if (p.res != nullptr) load_res(chunk_begin);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (c < chunk_begin || c >= chunk_end) continue;
+    if (n0 + c * 32 >= p.N) break;
+    uint32_t v[32];
+    tmem_ld32(t_addr + uint32_t(c * 32), v);
+    float4 rc[8];
+    if (p.res != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) rc[j] = rn[j];
+      if (c + 1 < chunk_end) load_res(c + 1);
+    }
+    tc_wait_ld();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), oscale, __shfl_sync(0xffffffffu, bias_r[c], j));
+    if (p.res != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { f[4 * j] += rc[j].x; f[4 * j + 1] += rc[j].y; f[4 * j + 2] += rc[j].z; f[4 * j + 3] += rc[j].w; }
+    }
+    if (ACT == 1) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
+    }
+    uint8_t* buf = stage;
+    if (lane == 0) tma_store_wait_read<0>();  // the previous chunk's store has finished reading the staging block
+    __syncwarp();
+    if (OUT_HALF) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        __half2 h0 = __floats2half2_rn(f[8 * j], f[8 * j + 1]), h1 = __floats2half2_rn(f[8 * j + 2], f[8 * j + 3]);
+        __half2 h2 = __floats2half2_rn(f[8 * j + 4], f[8 * j + 5]), h3 = __floats2half2_rn(f[8 * j + 6], f[8 * j + 7]);
+        uint4 pk;
+        pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+        pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(buf + lane * 64 + j * 16) = pk;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+      tma_store_3d(tmC, buf, n0 + c * 32, row0, bt);
+      tma_store_commit();
+    }
+  }
+}
+
+// bias of the tile's columns, one value per lane and 32-column chunk; loaded before the accumulator is ready
+template <int BN>
+__device__ __forceinline__ void gemm_load_bias(const GemmParams& p, int n0, int lane, float (&bias_r)[BN / 32]) {
+#pragma unroll
+  for (int c = 0; c < BN / 32; ++c) {
+    const int col = n0 + c * 32 + lane;
+    bias_r[c] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.f;
+  }
 }
 
 template <int BN, bool OUT_HALF, int ACT>
-__global__ void __launch_bounds__(256, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using Cfg = GemmCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint8_t* epi_stage = smem + S * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + GEMM_EPI_SMEM);
   uint64_t* full = bars;
   uint64_t* empty = bars + S;
   uint64_t* tfull = bars + 2 * S;
@@ -148,6 +163,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -156,8 +172,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 4);
-    mbar_init(&tempty[1], 4);
+    mbar_init(&tempty[0], GEMM_EPI_WARPS);
+    mbar_init(&tempty[1], GEMM_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -223,17 +239,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                       // TMEM lane quadrant of this warp
     const float oscale = (p.out_scale != 0.f) ? p.out_scale : 1.0f;
+    uint8_t* my_stage = epi_stage + (warp - 4) * 4096;
+    constexpr int NCH = BN / 32, SPLIT = (NCH + 1) / 2;
+    const int cb = (warp < 8) ? 0 : SPLIT, ce = (warp < 8) ? SPLIT : NCH;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int bt = t / tiles_mn, tt = t % tiles_mn;
       const int m0 = (tt % p.tiles_m) * GEMM_BM;
       const int n0 = (tt / p.tiles_m) * BN;
-      const int row = m0 + q * 32 + lane;
+      float bias_r[BN / 32];
+      gemm_load_bias<BN>(p, n0, lane, bias_r);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      gemm_epilogue_tile<BN, OUT_HALF, ACT>(p, t_addr, row, n0, bt, oscale);
+      gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, bt, oscale, my_stage, lane, bias_r, cb, ce);
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -241,6 +261,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();

@@ -11,7 +11,7 @@
 //   full[s]   : leader's barrier, armed by the leader's producer with the bytes of BOTH CTAs; both producers' TMA
 //               loads complete_tx on it (the peer addresses it through mapa).
 //   empty[s]  : one per CTA; tcgen05.commit.multicast from the leader releases the slot in both CTAs.
-//   tfull[a]  : one per CTA (multicast commit); tempty[a]: leader's, 8 arrivals (4 epilogue warps x 2 CTAs).
+//   tfull[a]  : one per CTA (multicast commit); tempty[a]: leader's, 16 arrivals (8 epilogue warps x 2 CTAs).
 #pragma once
 #include "gemm_tc.cuh"
 
@@ -20,19 +20,22 @@ namespace samrs {
 template <int BN>
 struct Gemm2Cfg {
   static constexpr int kStageBytes = GEMM_BM * 128 + (BN / 2) * 128;     // per CTA
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kStages = (226 * 1024 - 1280 - GEMM_EPI_SMEM) / kStageBytes > 8 ? 8 : (226 * 1024 - 1280 - GEMM_EPI_SMEM) / kStageBytes;
   static constexpr int kTmemCols = (2 * BN <= 256) ? 256 : 512;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + GEMM_EPI_SMEM;
 };
 
 template <int BN, bool OUT_HALF, int ACT>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(256, 1)
-gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
+  if (threadIdx.x == 0) gemm_dbg(p, 0);
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint8_t* epi_stage = smem + S * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + GEMM_EPI_SMEM);
   uint64_t* full = bars;
   uint64_t* empty = bars + S;
   uint64_t* tfull = bars + 2 * S;
@@ -49,6 +52,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmC);
   }
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
@@ -57,8 +61,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
-    mbar_init(&tempty[0], 8);
-    mbar_init(&tempty[1], 8);
+    mbar_init(&tempty[0], 2 * GEMM_EPI_WARPS);
+    mbar_init(&tempty[1], 2 * GEMM_EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc_pair<Cfg::kTmemCols>(tmem_slot);
@@ -66,6 +70,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   cluster_sync_all();                               // barriers of both CTAs initialised before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) gemm_dbg(p, 1);
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs)
@@ -93,15 +98,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       constexpr uint32_t idesc = umma_idesc_f16(256, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
-      int as = 0;
+      int as = 0, ti = 0;
       uint32_t aphase = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
+        gemm_dbg(p, 16 + ti * 64 + 0);
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
+        gemm_dbg(p, 16 + ti * 64 + 1);
         const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (kb < 40) gemm_dbg(p, 16 + ti * 64 + 2 + kb);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + GEMM_BM * 128;
           const uint64_t da = umma_desc_sw128(sa);
@@ -113,6 +121,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
         tc_commit_pair(&tfull[as], 0x3);
+        gemm_dbg(p, 16 + ti * 64 + 60);
+        ++ti;
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -121,26 +131,36 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ---------------------------------------------------------------- epilogue (both CTAs, own 128 rows)
     const int q = warp & 3;
     const float oscale = (p.out_scale != 0.f) ? p.out_scale : 1.0f;
-    int as = 0;
+    uint8_t* my_stage = epi_stage + (warp - 4) * 4096;
+    constexpr int NCH = BN / 32, SPLIT = (NCH + 1) / 2;
+    const int cb = (warp < 8) ? 0 : SPLIT, ce = (warp < 8) ? SPLIT : NCH;
+    int as = 0, eti = 0;
     uint32_t aphase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int m0 = (t % p.tiles_m) * 256 + int(rank) * GEMM_BM;
       const int n0 = (t / p.tiles_m) * BN;
-      const int row = m0 + q * 32 + lane;
+      float bias_r[BN / 32];
+      gemm_load_bias<BN>(p, n0, lane, bias_r);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+      if (warp == 4 && lane == 0) gemm_dbg(p, 16 + eti * 64 + 61);
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      gemm_epilogue_tile<BN, OUT_HALF, ACT>(p, t_addr, row, n0, 0, oscale);
+      gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, 0, oscale, my_stage, lane, bias_r, cb, ce);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[as], 0));
+      if (warp == 4 && lane == 0) gemm_dbg(p, 16 + eti * 64 + 62);
+      ++eti;
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
+    if (lane == 0) tma_store_wait_all();
   }
 
   tc_fence_before();
+  if (threadIdx.x == 0) gemm_dbg(p, 2);
   cluster_sync_all();                               // nobody exits (or frees TMEM) while the pair still signals
+  if (threadIdx.x == 0) gemm_dbg(p, 3);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
