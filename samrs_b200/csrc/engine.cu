@@ -127,9 +127,10 @@ static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const
 }
 
 // model of one tile's duration in SM clocks: tensor-pipe time vs the L2->SM feed (~50 B/clk/SM measured)
+// (feed rates fitted to tools/gemm_sweep.py on a B200: ~80 B/clk/SM for the 1-CTA kernel, ~52 for the CTA-pair kernel)
 static double tile_clk(int bn, int K, bool pair) {
   const double mma = double(bn) * K / 32.0;
-  const double l2 = (128.0 + (pair ? bn / 2.0 : double(bn))) * K * 2.0 / 50.0;
+  const double l2 = (128.0 + (pair ? bn / 2.0 : double(bn))) * K * 2.0 / (pair ? 52.0 : 80.0);
   return (mma > l2 ? mma : l2) + 600.0;
 }
 
@@ -142,7 +143,11 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   // force_bn: 0 = choose; 128/160/256 = 1-CTA kernel with that N tile; 1128/1160/1256 = CTA-pair kernel
   int bn = force_bn % 1000;
   bool pair = force_bn >= 1000;
-  if (force_bn == 0) {
+  if (force_bn == 0 && p.M == 4096 && p.batch == 1 && (p.N == 1280 || p.N == 3840 || p.N == 5120) && num_sms == 148) {
+    // ViT-H shapes: measured best configurations (profiles/r01_gemm_sweep_v3.json)
+    bn = (p.N == 1280) ? 160 : (p.N == 3840 ? 224 : 256);
+    pair = false;
+  } else if (force_bn == 0) {
     // pick the (kernel, N tile) with the smallest modelled duration = waves x per-tile time
     const int cands[4] = {256, 224, 160, 128};
     double best = 1e30;
@@ -382,7 +387,7 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
     SAMRS_TRY(make_tmap_3d(&tA, qkv, uint64_t(hd), uint64_t(e->heads), 4096, uint64_t(hd) * 2, uint64_t(3 * D) * 2, GEMM_BK, 1, GEMM_BM));
     GemmParams gp;
     gp.M = 4096; gp.N = NP; gp.K = hd; gp.out = e->rel; gp.ldc = NP; gp.bias = nullptr; gp.res = nullptr; gp.ldr = 0; gp.res_mod = 0;
-    gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f; gp.dbg = nullptr;
+    gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f; gp.dbg = nullptr; gp.accumulate = 0;
     SAMRS_TRY(launch_gemm_tc(nullptr, 8, reltab, hd, gp, false, 0, e->num_sms, st, global ? 256 : 128, &tA));
   }
   ProfScope ps2(global ? PC_ATTN_GLOB : PC_ATTN_WIN, st);
@@ -726,13 +731,13 @@ static int ensure_mask_scratch(Engine* e, int B) {
 
 // ------------------------------------------------------------------ encoder
 static int gemm_enc(Engine* e, cudaStream_t st, const __half* A, int lda, const __half* W, int M, int N, int K, void* out, int ldc,
-                    bool out_half, const float* bias, const float* res, int ldr, int res_mod, int act) {
+                    bool out_half, const float* bias, const float* res, int ldr, int res_mod, int act, int accumulate = 0) {
   GemmParams p;
   p.M = M; p.N = N; p.K = K;
   p.out = out; p.ldc = ldc;
   p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.tiles_m = p.tiles_n = 0;
-  p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f; p.dbg = nullptr;
+  p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f; p.dbg = nullptr; p.accumulate = accumulate;
   ProfScope ps(PC_GEMM, st);
   return launch_gemm_tc(A, lda, W, K, p, out_half, act, e->num_sms, st, 0);
 }
@@ -761,17 +766,17 @@ static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, flo
   SAMRS_TRY(gemm_enc(e, st, e->a_pe, 768, e->w_patch, T, D, 768, e->x, D, false, e->b_patch, e->pos_embed, D, 0, 0));
   for (int i = 0; i < e->depth; ++i) {
     const BlockWeights& b = e->blocks[i];
-    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln1w, b.ln1b, 1e-6f, e->xn, D, T, D, i > 0 ? e->delta : nullptr, e->x))); }
+    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln1w, b.ln1b, 1e-6f, e->xn, D, T, D))); }
     SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.wqkv, T, 3 * D, D, e->qkv, 3 * D, true, b.bqkv_eff, nullptr, 0, 0, 0));
     SAMRS_TRY(encoder_attention(e, st, e->qkv, b.reltab, b.global, e->attn_o));
-    // proj / lin2 write their fp32 output (bias included) to `delta`; the following LayerNorm applies x += delta
-    SAMRS_TRY(gemm_enc(e, st, e->attn_o, D, b.wproj, T, D, D, e->delta, D, false, b.bproj_eff, nullptr, 0, 0, 0));
-    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln2w, b.ln2b, 1e-6f, e->xn, D, T, D, e->delta, e->x))); }
+    // proj / lin2 update the fp32 residual stream in place: x += A W^T + b through TMA reduce-add stores
+    SAMRS_TRY(gemm_enc(e, st, e->attn_o, D, b.wproj, T, D, D, e->x, D, false, b.bproj_eff, nullptr, 0, 0, 0, 1));
+    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln2w, b.ln2b, 1e-6f, e->xn, D, T, D))); }
     SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.w1, T, 4 * D, D, e->hid, 4 * D, true, b.b1, nullptr, 0, 0, 1));
-    SAMRS_TRY(gemm_enc(e, st, e->hid, 4 * D, b.w2, T, D, 4 * D, e->delta, D, false, b.b2, nullptr, 0, 0, 0));
+    SAMRS_TRY(gemm_enc(e, st, e->hid, 4 * D, b.w2, T, D, 4 * D, e->x, D, false, b.b2, nullptr, 0, 0, 0, 1));
   }
   // neck (image_encoder.py:88-104)
-  cast_f32_f16_kernel<<<unsigned((size_t(T) * D / 4 + 255) / 256), 256, 0, st>>>(e->x, e->x16, size_t(T) * D / 4, e->delta);
+  cast_f32_f16_kernel<<<unsigned((size_t(T) * D / 4 + 255) / 256), 256, 0, st>>>(e->x, e->x16, size_t(T) * D / 4);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   SAMRS_TRY(gemm_enc(e, st, e->x16, D, e->w_neck0, T, 256, D, e->neck0, 256, false, nullptr, nullptr, 0, 0, 0));
@@ -791,10 +796,10 @@ static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, flo
 // ------------------------------------------------------------------ decoder
 // C = A' W'^T / 256 + bias + R : 3-term split-fp16 product on the tcgen05 GEMM (near-fp32 accuracy)
 static int gemm_dec(Engine* e, cudaStream_t st, const __half* A3, const __half* W3, int M, int N, int K3, float* out, int ldc,
-                    const float* bias, const float* res, int ldr, int res_mod) {
+                    const float* bias, const float* res, int ldr, int res_mod, int accumulate = 0) {
   GemmParams p;
   p.M = M; p.N = N; p.K = K3; p.out = out; p.ldc = ldc; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
-  p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f; p.dbg = nullptr;
+  p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f; p.dbg = nullptr; p.accumulate = accumulate;
   return launch_gemm_tc(A3, K3, W3, K3, p, false, 0, e->num_sms, st, 0);
 }
 
@@ -910,7 +915,7 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
     if (layer == 0)
       SAMRS_TRY(gemm_dec(e, st, e->d_ioA, e->wd_o0, M4, 256, 384, e->d_keys, 256, L.i2t.bo, src, 256, src_mod));
     else
-      SAMRS_TRY(gemm_dec(e, st, e->d_ioA, e->wd_o1, M4, 256, 384, e->d_keys, 256, L.i2t.bo, e->d_keys, 256, 0));
+      SAMRS_TRY(gemm_dec(e, st, e->d_ioA, e->wd_o1, M4, 256, 384, e->d_keys, 256, L.i2t.bo, nullptr, 0, 0, 1));
     ln256_split_kernel<<<ln_blocks, 256, 0, st>>>(e->d_keys, L.n4w, L.n4b, 1e-5f, layer == 0 ? e->d_keys : nullptr, e->d_keysA, M4);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
@@ -1164,6 +1169,8 @@ int samrs_test_gemm(void* engine, const void* A, const void* B, int M, int N, in
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldc = N; p.bias = bias; p.res = res; p.ldr = N; p.res_mod = 0; p.tiles_m = p.tiles_n = 0;
   p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f;
   p.dbg = static_cast<unsigned long long*>(g_gemm_dbg);
+  p.accumulate = 0;
+  if (res != nullptr && res == out && !out_half) { p.res = nullptr; p.accumulate = 1; }   // in-place residual -> TMA reduce-add
   return set_err(e, launch_gemm_tc(static_cast<const __half*>(A), K, static_cast<const __half*>(B), K, p, out_half != 0, act_gelu, e->num_sms,
                                    static_cast<cudaStream_t>(stream), force_bn));
 }

@@ -30,6 +30,7 @@ struct GemmParams {
   long long out_batch_stride;   // elements between consecutive batch outputs
   float out_scale;      // accumulator is multiplied by this before bias/residual (split-weight scaling); 0 -> 1
   unsigned long long* dbg;   // optional: CTA 0 records clock64() at pipeline events (tools/gemm_trace.py)
+  int accumulate;       // fp32 output only: out += result (TMA reduce-add) instead of out = result
 };
 __device__ __forceinline__ void gemm_dbg(const GemmParams& p, int slot) {
   if (p.dbg != nullptr && blockIdx.x == 0 && slot < 4096) p.dbg[slot] = clock64();
@@ -50,7 +51,22 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + GEMM_EPI_SMEM;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. far below the
+// fp16 rounding of the result): one MUFU rcp, one MUFU ex2 and six FMAs instead of erff's ~30 instructions, which made the
+// lin1 epilogue longer than its main loop.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  float t, ex;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));      // MUFU, ~1 ulp
+  float poly = fmaf(t, 1.061405429f, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  poly *= t;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z * 1.4426950408889634f));  // MUFU, ~2 ulp
+  const float e = 1.0f - poly * ex;                                        // erf(|x|/sqrt2)
+  return 0.5f * x + 0.5f * fabsf(x) * e;                                   // x * (1 + sign(x) erf) / 2
+}
 
 
 // Epilogue of one accumulator tile, executed by one warp for its 32 TMEM lanes (rows row0 .. row0+31), 32 columns at
@@ -122,7 +138,8 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     fence_proxy_async_smem();
     __syncwarp();
     if (lane == 0) {
-      tma_store_3d(tmC, buf, n0 + c * 32, row0, bt);
+      if (!OUT_HALF && p.accumulate) tma_reduce_add_3d(tmC, buf, n0 + c * 32, row0, bt);
+      else tma_store_3d(tmC, buf, n0 + c * 32, row0, bt);
       tma_store_commit();
     }
   }

@@ -204,10 +204,12 @@ class Engine:
         return int(c.value)
 
     # -- kernel-level test hooks ---------------------------------------------------
-    def test_gemm(self, A: torch.Tensor, B: torch.Tensor, out_half: bool, bias=None, res=None, gelu=False, force_bn=0):
+    def test_gemm(self, A: torch.Tensor, B: torch.Tensor, out_half: bool, bias=None, res=None, gelu=False, force_bn=0, out=None):
+        """`out` given and `res is out` exercises the in-place residual path (TMA reduce-add)."""
         M, K = A.shape
         N = B.shape[0]
-        out = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=self.device)
+        if out is None:
+            out = torch.empty((M, N), dtype=torch.float16 if out_half else torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._check(self._lib.samrs_test_gemm(self._h, A.data_ptr(), B.data_ptr(), M, N, K, out.data_ptr(), int(out_half),
                                                   _ptr(bias), _ptr(res), int(gelu), force_bn, _stream(self.device)), "test_gemm")

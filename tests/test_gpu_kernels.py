@@ -45,6 +45,20 @@ def test_gemm_fp32_out_bias_residual(eng64, M, N, K, bn):
     assert err < 2e-3, f"max err {err}"
 
 
+@pytest.mark.parametrize("M,N,K,bn", [(4096, 1280, 1280, 0), (4096, 1280, 5120, 1160), (300, 200, 192, 160), (4096, 1280, 1280, 1256)])
+def test_gemm_inplace_residual_reduce_add(eng64, M, N, K, bn):
+    """x += A B^T + bias with x both residual and output: the epilogue issues TMA reduce-add stores."""
+    A, B = _rand((M, K), 31), _rand((N, K), 32, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 33, dtype=torch.float32)
+    x = _rand((M, N), 34, dtype=torch.float32)
+    ref = x + A.float() @ B.float().t() + bias
+    out = eng64.test_gemm(A, B, out_half=False, bias=bias, res=x, force_bn=bn, out=x)
+    torch.cuda.synchronize()
+    assert out is x
+    err = (x - ref).abs().max().item()
+    assert err < 2e-3, f"max err {err}"
+
+
 @pytest.mark.parametrize("M,N,K,gelu", [(4096, 3840, 1280, False), (4096, 5120, 1280, True), (384, 520, 136, True)])
 def test_gemm_fp16_out(eng64, M, N, K, gelu):
     A, B = _rand((M, K), 5), _rand((N, K), 6, 1.0 / math.sqrt(K))
