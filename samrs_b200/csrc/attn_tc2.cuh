@@ -1,0 +1,407 @@
+// tcgen05 attention, second generation: two softmax warpgroups per CTA ping-pong on one tensor core.
+//
+// Same mathematics as attn_tc.cuh (SA/modeling/image_encoder.py:224-240, 325-361; zero-filled padded keys, K/V bias
+// folded away), different schedule.  The first kernel ran   load -> S = QK^T -> softmax -> P (smem) -> O = PV -> rescale
+// strictly one after the other per query tile and reached ~0.1-0.18 PFLOP/s (profiles/r01_*).  Here:
+//   * a CTA owns TWO query tiles that share every K/V tile (windowed: the two halves of one 14x14 window and head;
+//     global: two adjacent 128-query tiles).  Warps 2-5 / 6-9 are the softmax warpgroups of tile 0 / 1; while one
+//     group is in its exp2 pass the tensor core works for the other.
+//   * P never touches shared memory: each softmax thread packs its row to fp16 and tcgen05.st's it over the first half
+//     of its own S columns; the PV MMA then reads A = P from tensor memory (tcgen05.mma with a TMEM A operand).
+//   * O accumulates in tensor memory across key tiles.  The running max used for scaling (m_ref) is only raised when
+//     a row's tile max exceeds it by more than 2^8 (P stays <= 256, far inside fp16); only then is O rescaled in TMEM.
+//     The exact result is independent of m_ref because O and the row sum l carry the same factor.
+// TMEM (512 columns): warpgroup w owns columns [256w, 256w+256): S at +0 (208 or 128 fp32 columns), P aliased on
+// S's first half, O at +112 (windowed: inside the dead upper half of S) or +128 (global).
+#pragma once
+#include <type_traits>
+
+#include "attn_tc.cuh"
+
+namespace samrs {
+
+template <int HD, int BX, int QBY, int KBY, int NKT>
+struct Attn2Cfg {
+  static constexpr int NATOM = (HD + 63) / 64;
+  static constexpr int KR = BX * KBY;
+  static constexpr int SN = (KR + 15) / 16 * 16;
+  static constexpr int QR = BX * QBY;
+  static constexpr int KV_STAGES = (NKT > 1) ? 2 : 1;
+  static constexpr int Q_TILE_BYTES = NATOM * 128 * 128;
+  static constexpr int KV_ATOM_BYTES = SN * 128;
+  static constexpr int KV_BYTES = NATOM * KV_ATOM_BYTES;
+  static constexpr int O_OFF = (NKT > 1) ? 128 : 112;
+  static constexpr int kSmemBytes = 2 * Q_TILE_BYTES + 2 * KV_STAGES * KV_BYTES + 1024 + 256;
+  static_assert(SN % 16 == 0 && SN <= 208, "bad S tile");
+  static_assert(O_OFF >= SN / 2 && O_OFF + HD <= 256, "O must not overlap P");
+};
+
+// compile-time loop: guarantees that every chunk offset is a constant, so relh[] / relw[] stay in registers
+template <int I, int N, int S, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + S, N, S>(f);
+  }
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int HD, int BX, int QBY, int KBY, int NKT>
+__global__ void __launch_bounds__(320, 1)
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+  using C = Attn2Cfg<HD, BX, QBY, KBY, NKT>;
+  constexpr int NATOM = C::NATOM, SN = C::SN, KR = C::KR, QR = C::QR, ST = C::KV_STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sQ = smem;                                   // [2 tiles][NATOM atoms][128 rows x 128 B]
+  uint8_t* sK = sQ + 2 * C::Q_TILE_BYTES;
+  uint8_t* sV = sK + ST * C::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * C::KV_BYTES);
+  uint64_t* q_full = bars + 0;
+  uint64_t* q_empty = bars + 1;
+  uint64_t* k_full = bars + 2;        // [2]
+  uint64_t* k_empty = bars + 4;
+  uint64_t* v_full = bars + 6;
+  uint64_t* v_empty = bars + 8;
+  uint64_t* s_full = bars + 10;       // [2] per warpgroup
+  uint64_t* p_full = bars + 12;       // [2] per warpgroup, 128 arrivals
+  uint64_t* o_full = bars + 14;       // [2] per warpgroup: last PV of the unit done
+  uint64_t* o_free = bars + 16;       // [2] per warpgroup, 128 arrivals: O has been read, S/O region reusable
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_units = p.num_qtiles * p.heads;         // num_qtiles = query-tile PAIRS here
+
+  for (int i = threadIdx.x; i < (2 * C::Q_TILE_BYTES + 2 * ST * C::KV_BYTES) / 16; i += blockDim.x)
+    reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  fence_proxy_async_smem();
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmKV);
+  }
+  if (warp == 1 && lane == 0) {
+    mbar_init(q_full, 1);
+    mbar_init(q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
+      mbar_init(&s_full[i], 1);
+      mbar_init(&p_full[i], 128);
+      mbar_init(&o_full[i], 1);
+      mbar_init(&o_free[i], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto unit_coords = [&](int unit, int& head, int& qy0, int& qy1, int& x0, int& ky0) {
+    head = unit % p.heads;
+    const int u = unit / p.heads;
+    if (NKT == 1) {              // windowed: u = window, the two tiles are its upper / lower 7 rows
+      x0 = (u % 5) * BX;
+      ky0 = (u / 5) * KBY;
+      qy0 = ky0;
+      qy1 = ky0 + QBY;
+    } else {                     // global: u = pair of 128-query tiles
+      x0 = 0;
+      ky0 = 0;
+      qy0 = u * 2 * QBY;
+      qy1 = qy0 + QBY;
+    }
+  };
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t qph = 0, kst = 0, kph = 0, vst = 0, vph = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        int head, qy0, qy1, x0, ky0;
+        unit_coords(unit, head, qy0, qy1, x0, ky0);
+        mbar_wait(q_empty, qph ^ 1);
+        mbar_expect_tx(q_full, 2 * NATOM * QR * 128);
+        for (int a = 0; a < NATOM; ++a) {
+          tma_load_3d(sQ + a * 128 * 128, &tmQ, q_full, head * HD + a * 64, x0, qy0);
+          tma_load_3d(sQ + C::Q_TILE_BYTES + a * 128 * 128, &tmQ, q_full, head * HD + a * 64, x0, qy1);
+        }
+        qph ^= 1;
+        for (int j = 0; j < NKT; ++j) {
+          mbar_wait(&k_empty[kst], kph ^ 1);
+          mbar_expect_tx(&k_full[kst], NATOM * KR * 128);
+          for (int a = 0; a < NATOM; ++a)
+            tma_load_3d(sK + kst * C::KV_BYTES + a * C::KV_ATOM_BYTES, &tmKV, &k_full[kst], p.D + head * HD + a * 64, x0, ky0 + j * KBY);
+          if (++kst == ST) { kst = 0; kph ^= 1; }
+          mbar_wait(&v_empty[vst], vph ^ 1);
+          mbar_expect_tx(&v_full[vst], NATOM * KR * 128);
+          for (int a = 0; a < NATOM; ++a)
+            tma_load_3d(sV + vst * C::KV_BYTES + a * C::KV_ATOM_BYTES, &tmKV, &v_full[vst], 2 * p.D + head * HD + a * 64, x0, ky0 + j * KBY);
+          if (++vst == ST) { vst = 0; vph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_f16(128, SN, 0, 0);
+      constexpr uint32_t idesc_o64 = umma_idesc_f16(128, 64, 0, 1);
+      constexpr uint32_t idesc_o16 = umma_idesc_f16(128, 16, 0, 1);
+      uint32_t qph = 0, kst = 0, kph = 0, vst = 0, vph = 0, pph[2] = {0, 0}, fph[2] = {0, 0};
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+      auto issue_s = [&](int w) {                       // S_w = Q_w K^T into warpgroup w's columns
+        const uint32_t d = tmem_base + uint32_t(w * 256);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t a = aQ + w * C::Q_TILE_BYTES + (k / 4) * (128 * 128) + (k % 4) * 32;
+          const uint32_t b = aK + kst * C::KV_BYTES + (k / 4) * C::KV_ATOM_BYTES + (k % 4) * 32;
+          tc_mma_f16(d, umma_desc_sw128(a), umma_desc_sw128(b), idesc_s, k != 0);
+        }
+        tc_commit(&s_full[w]);
+      };
+      auto issue_pv = [&](int w, int j) {               // O_w (+)= P_w V_j, A = P from tensor memory
+        const uint32_t d = tmem_base + uint32_t(w * 256 + C::O_OFF);
+        const uint32_t pa = tmem_base + uint32_t(w * 256);
+#pragma unroll
+        for (int k = 0; k < SN / 16; ++k) {
+          const uint32_t b = aV + vst * C::KV_BYTES + k * 2048;
+          const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
+          tc_mma_f16_ts(d, pa + uint32_t(k * 8), umma_desc_sw128(b), idesc_o64, acc);
+          if (NATOM == 2) tc_mma_f16_ts(d + 64, pa + uint32_t(k * 8), umma_desc_sw128(b + C::KV_ATOM_BYTES), idesc_o16, acc);
+        }
+      };
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+        mbar_wait(q_full, qph);
+        qph ^= 1;
+        mbar_wait(&k_full[kst], kph);
+        tc_fence_after();
+        for (int w = 0; w < 2; ++w) {                   // the warpgroup has read the previous unit's O (aliases S)
+          mbar_wait(&o_free[w], fph[w] ^ 1);
+          fph[w] ^= 1;
+          tc_fence_after();
+          issue_s(w);
+        }
+        tc_commit(&k_empty[kst]);
+        if (++kst == ST) { kst = 0; kph ^= 1; }
+        if (NKT == 1) tc_commit(q_empty);
+        for (int j = 0; j < NKT; ++j) {
+          const bool more = (j + 1 < NKT);
+          mbar_wait(&v_full[vst], vph);
+          if (more) mbar_wait(&k_full[kst], kph);
+          for (int w = 0; w < 2; ++w) {
+            mbar_wait(&p_full[w], pph[w]);
+            pph[w] ^= 1;
+            tc_fence_after();
+            issue_pv(w, j);
+            if (!more) tc_commit(&o_full[w]);
+            if (more) issue_s(w);                       // S_w of the next key tile overwrites the P it just consumed
+          }
+          tc_commit(&v_empty[vst]);
+          if (++vst == ST) { vst = 0; vph ^= 1; }
+          if (more) {
+            tc_commit(&k_empty[kst]);
+            if (++kst == ST) { kst = 0; kph ^= 1; }
+            if (j + 2 == NKT) tc_commit(q_empty);
+          }
+        }
+      }
+    }
+  } else if (warp >= 2) {
+    // ------------------------------------------------------------ softmax warpgroups (warps 2-5 and 6-9)
+    const int w = (warp - 2) >> 2;                      // warpgroup = query tile
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    const uint32_t wg_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(w * 256);
+    constexpr int NP = (BX == 64) ? 256 : 64;
+    constexpr int SS = BX;
+    uint32_t sph = 0, oph = 0;
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      int head, qy0, qy1, x0, ky0;
+      unit_coords(unit, head, qy0, qy1, x0, ky0);
+      const int qy = w ? qy1 : qy0;
+      const int ty = qy + r / BX, tx = x0 + r % BX;
+      const bool valid = (r < QR) && ty < 64 && tx < 64;
+      const int token = ty * 64 + tx;
+      const float* relrow = p.rel + (size_t(head) * 4096 + (valid ? token : 0)) * NP;
+      const int qh = qy - ky0 + r / BX, qw = r % BX;
+      float relw[BX];
+#pragma unroll
+      for (int i = 0; i < BX; ++i) relw[i] = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - i) : 0.f;
+      float m_ref = 0.f, l_run = 0.f;
+
+      for (int j = 0; j < NKT; ++j) {
+        float relh[KBY];
+#pragma unroll
+        for (int i = 0; i < KBY; ++i) relh[i] = valid ? __ldg(relrow + qh + (SS - 1) - ((NKT == 1 ? 0 : j * KBY) + i)) : 0.f;
+        mbar_wait(&s_full[w], sph);
+        sph ^= 1;
+        tc_fence_after();
+        // pass 1: row max of the biased, scaled scores (log2 domain)
+        float m_tile = -INFINITY;
+        static_for<0, SN, 32>([&](auto c0c) {
+          constexpr int c0 = decltype(c0c)::value;
+          if constexpr (SN - c0 >= 32) {
+            uint32_t v[32];
+            tmem_ld32(wg_addr + c0, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const int c = c0 + i;
+              if (c < KR) m_tile = fmaxf(m_tile, fmaf(__uint_as_float(v[i]), p.scale_log2e, relh[c / BX] + relw[c % BX]));
+            }
+          } else {
+            uint32_t v[16];
+            tmem_ld16(wg_addr + c0, v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+              const int c = c0 + i;
+              if (c < KR) m_tile = fmaxf(m_tile, fmaf(__uint_as_float(v[i]), p.scale_log2e, relh[c / BX] + relw[c % BX]));
+            }
+          }
+        });
+        if (j == 0) {
+          m_ref = m_tile;
+        } else {
+          // lazy rescale: s_full(j) also certifies that PV_{j-1} has completed, so O is quiescent here
+          const bool need = m_tile > m_ref + 8.0f;
+          if (__any_sync(0xffffffffu, need)) {
+            const float m_new = need ? m_tile : m_ref;
+            const float alpha = ex2_approx(m_ref - m_new);
+            static_for<0, HD, 32>([&](auto c0c) {
+              constexpr int c0 = decltype(c0c)::value;
+              if constexpr (HD - c0 >= 32) {
+                uint32_t v[32];
+                tmem_ld32(wg_addr + C::O_OFF + c0, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                tmem_st32(wg_addr + C::O_OFF + c0, v);
+              } else {
+                uint32_t v[16];
+                tmem_ld16(wg_addr + C::O_OFF + c0, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+                tmem_st16(wg_addr + C::O_OFF + c0, v);
+              }
+            });
+            l_run *= alpha;
+            m_ref = m_new;
+          }
+        }
+        // (opaque no-op: keeps the compiler from carrying all KR precomputed bias sums of pass 1 into pass 2, which
+        //  costs ~120 spilled registers; recomputing relh + relw is one FADD)
+#pragma unroll
+        for (int i = 0; i < BX; ++i) asm volatile("" : "+f"(relw[i]));
+        // pass 2: P = exp2(s - m_ref) -> fp16 pairs -> tensor memory (over the first half of this row's S columns)
+        float l_tile = 0.f;
+        static_for<0, SN, 32>([&](auto c0c) {
+          constexpr int c0 = decltype(c0c)::value;
+          if constexpr (SN - c0 >= 32) {
+            uint32_t v[32];
+            tmem_ld32(wg_addr + c0, v);
+            tc_wait_ld();
+            uint32_t pk[16];
+#pragma unroll
+            for (int i = 0; i < 32; i += 2) {
+              float e0 = 0.f, e1 = 0.f;
+              const int c = c0 + i;
+              if (c < KR) e0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, relh[c / BX] + relw[c % BX]) - m_ref);
+              if (c + 1 < KR) e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, relh[(c + 1) / BX] + relw[(c + 1) % BX]) - m_ref);
+              l_tile += e0 + e1;
+              __half2 h = __floats2half2_rn(e0, e1);
+              pk[i / 2] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            tmem_st16(wg_addr + c0 / 2, pk);
+          } else {
+            uint32_t v[16];
+            tmem_ld16(wg_addr + c0, v);
+            tc_wait_ld();
+            uint32_t pk[8];
+#pragma unroll
+            for (int i = 0; i < 16; i += 2) {
+              float e0 = 0.f, e1 = 0.f;
+              const int c = c0 + i;
+              if (c < KR) e0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, relh[c / BX] + relw[c % BX]) - m_ref);
+              if (c + 1 < KR) e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, relh[(c + 1) / BX] + relw[(c + 1) % BX]) - m_ref);
+              l_tile += e0 + e1;
+              __half2 h = __floats2half2_rn(e0, e1);
+              pk[i / 2] = *reinterpret_cast<uint32_t*>(&h);
+            }
+            tmem_st8(wg_addr + c0 / 2, pk);
+          }
+        });
+        l_run += l_tile;
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&p_full[w]);
+      }
+      // O complete: normalise and write the fp16 output row
+      mbar_wait(&o_full[w], oph);
+      oph ^= 1;
+      tc_fence_after();
+      const float inv = 1.0f / l_run;
+      __half* o = p.out + size_t(valid ? token : 0) * p.D + head * HD;
+      static_for<0, HD, 32>([&](auto c0c) {
+        constexpr int c0 = decltype(c0c)::value;
+        if constexpr (HD - c0 >= 32) {
+          uint32_t v[32];
+          tmem_ld32(wg_addr + C::O_OFF + c0, v);
+          tc_wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 8) {
+              __half2 h0 = __floats2half2_rn(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+              __half2 h1 = __floats2half2_rn(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+              __half2 h2 = __floats2half2_rn(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+              __half2 h3 = __floats2half2_rn(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(o + c0 + i) = pk;
+            }
+          }
+        } else {
+          uint32_t v[16];
+          tmem_ld16(wg_addr + C::O_OFF + c0, v);
+          tc_wait_ld();
+          if (valid) {
+#pragma unroll
+            for (int i = 0; i < 16; i += 8) {
+              __half2 h0 = __floats2half2_rn(__uint_as_float(v[i]) * inv, __uint_as_float(v[i + 1]) * inv);
+              __half2 h1 = __floats2half2_rn(__uint_as_float(v[i + 2]) * inv, __uint_as_float(v[i + 3]) * inv);
+              __half2 h2 = __floats2half2_rn(__uint_as_float(v[i + 4]) * inv, __uint_as_float(v[i + 5]) * inv);
+              __half2 h3 = __floats2half2_rn(__uint_as_float(v[i + 6]) * inv, __uint_as_float(v[i + 7]) * inv);
+              uint4 pk;
+              pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+              pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+              *reinterpret_cast<uint4*>(o + c0 + i) = pk;
+            }
+          }
+        }
+      });
+      tc_fence_before();
+      mbar_arrive(&o_free[w]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace samrs

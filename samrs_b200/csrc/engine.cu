@@ -9,6 +9,7 @@
 
 #include "../../include/samrs_b200.h"
 #include "attn_tc.cuh"
+#include "attn_tc2.cuh"
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
@@ -374,6 +375,22 @@ static int launch_attn_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, const
   return 0;
 }
 
+template <int HD, int BX, int QBY, int KBY, int NKT>
+static int launch_attn2_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, const AttnParams& p, int num_sms, cudaStream_t st) {
+  using C = Attn2Cfg<HD, BX, QBY, KBY, NKT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAMRS_CUDA_OK(cudaFuncSetAttribute(attn_tc2_kernel<HD, BX, QBY, KBY, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
+    attr_done = true;
+  }
+  const int units = p.num_qtiles * p.heads;
+  const int grid = units < num_sms ? units : num_sms;
+  attn_tc2_kernel<HD, BX, QBY, KBY, NKT><<<grid, 320, C::kSmemBytes, st>>>(tQ, tKV, p);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
 // encoder attention of one block: rel-pos terms + tcgen05 attention.  qkv: [4096][3D] fp16.
 static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, const __half* reltab, bool global, __half* out) {
   const int D = e->D, hd = e->hd;
@@ -399,16 +416,27 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
   p.scale_log2e = (1.0f / sqrtf(float(hd))) * 1.4426950408889634f;
   CUtensorMap tQ, tKV;
   const uint64_t pitch_x = uint64_t(3 * D) * 2, pitch_y = pitch_x * 64;
+  static const bool attn_v1 = getenv("SAMRS_ATTN_V1") != nullptr;     // first-generation kernel (one query tile per CTA)
   if (global) {
     p.num_qtiles = 32;
     SAMRS_TRY(make_tmap_3d(&tQ, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 64, 2));
     tKV = tQ;
+    if (!attn_v1) {
+      p.num_qtiles = 16;                                              // pairs of 128-query tiles
+      if (hd == 64) return launch_attn2_inst<64, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
+      return launch_attn2_inst<80, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
+    }
     if (hd == 64) return launch_attn_inst<64, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
     return launch_attn_inst<80, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
   }
   p.num_qtiles = 50;
   SAMRS_TRY(make_tmap_3d(&tQ, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 14, 7));
   SAMRS_TRY(make_tmap_3d(&tKV, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 14, 14));
+  if (!attn_v1) {
+    p.num_qtiles = 25;                                                // windows (two 7-row halves each)
+    if (hd == 64) return launch_attn2_inst<64, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
+    return launch_attn2_inst<80, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
+  }
   if (hd == 64) return launch_attn_inst<64, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
   return launch_attn_inst<80, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
 }

@@ -1,0 +1,116 @@
+"""CPU tests of the host-side logic: checkpoint layout, synthetic inputs, coordinate transforms, tile sharding."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from samrs_b200 import synth
+from samrs_b200.config import GEOMETRIES, geometry
+from samrs_b200.stream import pack_state_dict, packed_numel, shard_indices, unpack_state_dict
+from samrs_b200.weights import check_state_dict, state_dict_spec, synthetic_state_dict
+
+
+def test_geometries_match_reference_registry():
+    # segment_anything/build_sam.py:14-44
+    assert (geometry("vit_h").embed_dim, geometry("vit_h").depth, geometry("vit_h").num_heads) == (1280, 32, 16)
+    assert geometry("vit_h").global_attn_indexes == (7, 15, 23, 31)
+    assert (geometry("vit_l").embed_dim, geometry("vit_l").depth, geometry("vit_l").global_attn_indexes) == (1024, 24, (5, 11, 17, 23))
+    assert (geometry("vit_b").embed_dim, geometry("vit_b").depth, geometry("vit_b").global_attn_indexes) == (768, 12, (2, 5, 8, 11))
+    assert GEOMETRIES["default"] is GEOMETRIES["vit_h"]
+    with pytest.raises(KeyError):
+        geometry("vit_x")
+
+
+def test_state_dict_spec_counts():
+    # 594 tensors / 641 090 864 parameters for ViT-H, 314 tensors for ViT-B
+    spec = state_dict_spec(geometry("vit_h"))
+    assert len(spec) == 594
+    assert sum(int(np.prod(s)) for _, s, _ in spec) == 641_090_864
+    assert len(state_dict_spec(geometry("vit_b"))) == 314
+    assert len({k for k, _, _ in spec}) == len(spec)
+
+
+def test_synthetic_checkpoint_is_deterministic_and_strict():
+    a, b = synthetic_state_dict("vit_t64", 0), synthetic_state_dict("vit_t64", 0)
+    c = synthetic_state_dict("vit_t64", 1)
+    assert all(torch.equal(a[k], b[k]) for k in a)
+    assert any(not torch.equal(a[k], c[k]) for k in a)
+    # parameters the reference zero-initialises are exercised
+    assert a["image_encoder.blocks.0.attn.rel_pos_h"].abs().max() > 0
+    assert a["image_encoder.pos_embed"].abs().max() > 0
+    check_state_dict("vit_t64", a)
+    bad = dict(a)
+    bad.pop("mask_decoder.iou_token.weight")
+    with pytest.raises(RuntimeError, match="missing"):
+        check_state_dict("vit_t64", bad)
+    bad = dict(a)
+    bad["image_encoder.neck.0.weight"] = torch.zeros(3)
+    with pytest.raises(RuntimeError, match="size mismatch"):
+        check_state_dict("vit_t64", bad)
+
+
+def test_pack_unpack_roundtrip():
+    g = geometry("vit_t80")
+    sd = synthetic_state_dict("vit_t80", 3)
+    flat = pack_state_dict(g, sd, torch.empty(packed_numel(g)))
+    back = unpack_state_dict(g, flat)
+    assert list(back) == list(sd)
+    assert all(torch.equal(back[k], sd[k]) for k in sd)
+
+
+def test_synthetic_inputs():
+    t = synth.tile(5)
+    assert t.shape == (1024, 1024, 3) and t.dtype == np.uint8 and np.array_equal(t, synth.tile(5))
+    b = synth.hboxes(5, 32)
+    assert b.shape == (32, 4) and b.dtype == np.float32
+    assert (b[:, 2] >= b[:, 0]).all() and (b[:, 3] >= b[:, 1]).all() and b.min() >= 0 and b.max() <= 1023
+    tiny = synth.hboxes(5, 64, tiny=True)
+    assert ((tiny[:, 2] - tiny[:, 0]) <= 32).all()
+    lab = synth.labels(5, 32)
+    assert lab.min() >= 0 and lab.max() < 18
+    assert synth.rboxes_5pt(5, 8).shape == (8, 5, 2)
+    m = synth.mask_prompts(5, 2)
+    assert m.shape == (2, 1, 256, 256) and set(np.unique(m)) == {-1000.0, 1000.0}
+
+
+def test_shard_indices_cover_disjointly():
+    for world in (1, 2, 3, 8):
+        seen = []
+        for r in range(world):
+            seen += shard_indices(37, r, world)
+        assert sorted(seen) == list(range(37))
+    assert shard_indices(10, 1, 4) == [1, 5, 9]
+    with pytest.raises(ValueError):
+        shard_indices(10, 4, 4)
+
+
+def test_resize_longest_side_matches_oracle_and_reference_rule():
+    """segment_anything/utils/transforms.py:83-102: boxes scale by (new/old) of the long-side-1024 resize."""
+    import samrs_b200
+    sys.path.insert(0, samrs_b200.DROPIN_PATH)
+    try:
+        for k in [k for k in sys.modules if k == "segment_anything" or k.startswith("segment_anything.")]:
+            del sys.modules[k]
+        from segment_anything.utils.transforms import ResizeLongestSide
+        from oracle import sam_oracle as O
+        tr = ResizeLongestSide(1024)
+        assert tr.get_preprocess_shape(800, 800, 1024) == (1024, 1024)
+        assert tr.get_preprocess_shape(600, 800, 1024) == (768, 1024)
+        assert tr.get_preprocess_shape(1500, 1000, 1024) == (1024, 683)
+        boxes = torch.tensor([[10.0, 20.0, 300.0, 400.0], [0.0, 0.0, 799.0, 599.0]], dtype=torch.float64)
+        out = tr.apply_boxes_torch(boxes, (600, 800))
+        assert out.dtype == torch.float32
+        assert torch.allclose(out, O.apply_boxes(boxes, (600, 800)))
+        assert torch.equal(boxes, torch.tensor([[10.0, 20.0, 300.0, 400.0], [0.0, 0.0, 799.0, 599.0]], dtype=torch.float64))
+        img = synth.tile(1)
+        assert tr.apply_image(img) is not None and np.array_equal(tr.apply_image(img), img)      # identity at 1024^2
+        small = synth.tile(2)[:600, :800]
+        assert tr.apply_image(small).shape == (768, 1024, 3)
+        pts = np.array([[[1.0, 2.0]]])
+        assert np.allclose(tr.apply_coords(pts, (512, 512)), pts * 2)
+    finally:
+        sys.path.remove(samrs_b200.DROPIN_PATH)
+        for k in [k for k in sys.modules if k == "segment_anything" or k.startswith("segment_anything.")]:
+            del sys.modules[k]
