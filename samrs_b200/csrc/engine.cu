@@ -282,7 +282,7 @@ struct Engine {
 
   // encoder activations
   __half *a_pe, *xn, *qkv, *attn_o, *hid, *x16, *neck_ln16, *neck_col;
-  float *x, *delta, *rel, *neck0, *neck2, *feat_tok, *feat_nchw;
+  float *x, *rel, *neck0, *neck2, *feat_tok, *feat_nchw;
   // per-image decoder cache
   float *src0, *K0, *V0, *Qi0;
   float* pp_full = nullptr;            // postprocess scratch for non-1024 sizes
@@ -344,15 +344,15 @@ static int sgemm(cudaStream_t st, const float* A, int lda, const float* W, int l
 
 template <typename OutT, int ACT>
 static int ln_rows(cudaStream_t st, const float* in, int ld_in, const float* g, const float* b, float eps, OutT* out, int ld_out,
-                   int rows, int C, const float* add = nullptr, float* x_out = nullptr) {
+                   int rows, int C) {
   const int nv = C / 4;
   const int threads = 256, rows_per_block = threads / 32;
   const int grid = (rows + rows_per_block - 1) / rows_per_block;
   if (C % 4 != 0) SAMRS_FAIL("layernorm: C must be a multiple of 4");
-  if (nv <= 32) ln_rows_kernel<OutT, ACT, 1><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C, add, x_out);
-  else if (nv <= 64) ln_rows_kernel<OutT, ACT, 2><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C, add, x_out);
-  else if (nv <= 192) ln_rows_kernel<OutT, ACT, 6><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C, add, x_out);
-  else if (nv <= 320) ln_rows_kernel<OutT, ACT, 10><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C, add, x_out);
+  if (nv <= 32) ln_rows_kernel<OutT, ACT, 1><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
+  else if (nv <= 64) ln_rows_kernel<OutT, ACT, 2><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
+  else if (nv <= 192) ln_rows_kernel<OutT, ACT, 6><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
+  else if (nv <= 320) ln_rows_kernel<OutT, ACT, 10><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
   else SAMRS_FAIL("layernorm: C too large");
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -691,7 +691,6 @@ static int alloc_activations(Engine* e) {
   const size_t D = e->D, T = 4096;
   SAMRS_TRY(e->alloc(&e->a_pe, T * 768));
   SAMRS_TRY(e->alloc(&e->x, T * D));
-  SAMRS_TRY(e->alloc(&e->delta, T * D));
   SAMRS_TRY(e->alloc(&e->xn, T * D));
   SAMRS_TRY(e->alloc(&e->qkv, T * 3 * D));
   SAMRS_TRY(e->alloc(&e->rel, size_t(e->heads) * T * 256));

@@ -43,12 +43,10 @@ __global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, int H,
 // two-pass mean / biased variance in registers.  OutT = __half feeds the next tensor-core GEMM,
 // OutT = float is used by the decoder.  ACT 1 = GELU(erf) (output_upscaling, mask_downscaling).
 // ------------------------------------------------------------------------------------------------
-// `add` (optional) is the previous GEMM's fp32 output: the residual update x += add is fused here (x_out gets the
-// sum) so that the GEMM epilogues never read the residual stream (see profiles/r01_gemm_trace.txt).
 template <typename OutT, int ACT, int MAXV /* float4 per lane */>
-__global__ void ln_rows_kernel(const float* in, int ld_in, const float* __restrict__ gamma,
-                               const float* __restrict__ beta, float eps, OutT* out, int ld_out,
-                               int rows, int C, const float* __restrict__ add, float* x_out /* may alias in */) {
+__global__ void ln_rows_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ gamma,
+                               const float* __restrict__ beta, float eps, OutT* __restrict__ out, int ld_out,
+                               int rows, int C) {
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (warp >= rows) return;
@@ -60,11 +58,6 @@ __global__ void ln_rows_kernel(const float* in, int ld_in, const float* __restri
   for (int i = 0; i < MAXV; ++i) {
     const int k = lane + 32 * i;
     v[i] = (k < nv) ? src[k] : make_float4(0, 0, 0, 0);
-    if (add != nullptr && k < nv) {
-      const float4 a = reinterpret_cast<const float4*>(add + size_t(warp) * ld_in)[k];
-      v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
-      reinterpret_cast<float4*>(x_out + size_t(warp) * ld_in)[k] = v[i];
-    }
     s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
   }
 #pragma unroll
@@ -106,15 +99,11 @@ __global__ void ln_rows_kernel(const float* in, int ld_in, const float* __restri
   }
 }
 
-// fp32 (+ optional fp32 addend) -> fp16 cast of a contiguous buffer (n multiple of 4)
-__global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n4, const float* __restrict__ add = nullptr) {
+// fp32 -> fp16 cast of a contiguous buffer (n multiple of 4)
+__global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n4) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n4) return;
-  float4 v = reinterpret_cast<const float4*>(in)[i];
-  if (add != nullptr) {
-    const float4 a = reinterpret_cast<const float4*>(add)[i];
-    v.x += a.x; v.y += a.y; v.z += a.z; v.w += a.w;
-  }
+  const float4 v = reinterpret_cast<const float4*>(in)[i];
   __half2 h0 = __floats2half2_rn(v.x, v.y), h1 = __floats2half2_rn(v.z, v.w);
   uint2 pk;
   pk.x = *reinterpret_cast<uint32_t*>(&h0);
