@@ -31,7 +31,11 @@ struct AttnParams {
   int heads;
   int num_qtiles;       // windowed: 25 windows * 2 halves; global: 32
   float scale_log2e;    // hd^-0.5 * log2(e)
+  unsigned long long* dbg;   // optional pipeline trace of CTA 0 (tools/attn_trace.py)
 };
+__device__ __forceinline__ void attn_dbg(const AttnParams& p, int slot) {
+  if (p.dbg != nullptr && blockIdx.x == 0 && slot < 4096) p.dbg[slot] = clock64();
+}
 
 template <int HD, int BX, int QBY, int KBY, int NKT>
 struct AttnCfg {

@@ -4,15 +4,20 @@
 // folded away), different schedule.  The first kernel ran   load -> S = QK^T -> softmax -> P (smem) -> O = PV -> rescale
 // strictly one after the other per query tile and reached ~0.1-0.18 PFLOP/s (profiles/r01_*).  Here:
 //   * a CTA owns TWO query tiles that share every K/V tile (windowed: the two halves of one 14x14 window and head;
-//     global: two adjacent 128-query tiles).  Warps 2-5 / 6-9 are the softmax warpgroups of tile 0 / 1; while one
+//     global: two adjacent 128-query tiles).  Warps 4-7 / 8-11 are the softmax warpgroups of tile 0 / 1; while one
 //     group is in its exp2 pass the tensor core works for the other.
 //   * P never touches shared memory: each softmax thread packs its row to fp16 and tcgen05.st's it over the first half
 //     of its own S columns; the PV MMA then reads A = P from tensor memory (tcgen05.mma with a TMEM A operand).
 //   * O accumulates in tensor memory across key tiles.  The running max used for scaling (m_ref) is only raised when
 //     a row's tile max exceeds it by more than 2^8 (P stays <= 256, far inside fp16); only then is O rescaled in TMEM.
 //     The exact result is independent of m_ref because O and the row sum l carry the same factor.
+//   * the decomposed rel-pos bias is added by the tensor core, not by the softmax threads: bias[q,k] = R[q,:] . E[k,:]
+//     with R the query's rel-pos terms (fp16, written once per unit into TMEM by the row's thread) and E a constant
+//     one-hot matrix in shared memory (global: E[k][kw'] = [k mod 64 == kw'], the two relh terms of a key tile stay
+//     scalar; windowed: E[k][kh'] = [k div 14 == kh'], E[k][14+kw'] = [k mod 14 == kw']).  One extra MMA per key tile
+//     (K = 64 / 32) replaces a load + add per score, which halves the instruction count of both softmax passes.
 // TMEM (512 columns): warpgroup w owns columns [256w, 256w+256): S at +0 (208 or 128 fp32 columns), P aliased on
-// S's first half, O at +112 (windowed: inside the dead upper half of S) or +128 (global).
+// S's first half, O at +112 (windowed: inside the dead upper half of S) or +128 (global), R at +208.
 #pragma once
 #include <type_traits>
 
@@ -31,7 +36,10 @@ struct Attn2Cfg {
   static constexpr int KV_ATOM_BYTES = SN * 128;
   static constexpr int KV_BYTES = NATOM * KV_ATOM_BYTES;
   static constexpr int O_OFF = (NKT > 1) ? 128 : 112;
-  static constexpr int kSmemBytes = 2 * Q_TILE_BYTES + 2 * KV_STAGES * KV_BYTES + 1024 + 256;
+  static constexpr int R_OFF = 208;                          // TMEM column of the packed fp16 rel-pos operand R
+  static constexpr int RK = (NKT > 1) ? 64 : 32;             // K extent of the bias MMA (kw' | kh',kw')
+  static constexpr int E_BYTES = SN * 128;                   // one-hot matrix E: SN key rows x 64 fp16 (SW128 atom rows)
+  static constexpr int kSmemBytes = 2 * Q_TILE_BYTES + 2 * KV_STAGES * KV_BYTES + E_BYTES + 1024 + 256;
   static_assert(SN % 16 == 0 && SN <= 208, "bad S tile");
   static_assert(O_OFF >= SN / 2 && O_OFF + HD <= 256, "O must not overlap P");
 };
@@ -51,8 +59,27 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// exp2 on the FMA / integer pipes (Cody-Waite split + degree-4 polynomial on [-0.5, 0.5], relative error 3.6e-6, far
+// below the fp16 rounding of P).  The MUFU unit retires one warp-wide ex2 per 8 clocks per SM sub-partition and the
+// softmax warps were bound by it (and by the fp32->fp16 packs that share it): every third exponential goes here.
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -125.0f);
+  const float r = x + 12582912.0f;                 // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
+  const float f = x - (r - 12582912.0f);           // fractional part in [-0.5, 0.5]
+  float q = fmaf(f, 0.009676037f, 0.055922036f);
+  q = fmaf(q, f, 0.24022107f);
+  q = fmaf(q, f, 0.69312103f);
+  q = fmaf(q, f, 1.0000001f);
+  return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
+}
+template <int I>
+__device__ __forceinline__ float ex2_mixed(float x) {
+  if constexpr (false && I % 3 == 2) return ex2_poly(x);   // measured: no gain (the global kernel is issue-bound), kept for reference
+  else return ex2_approx(x);
+}
+
 template <int HD, int BX, int QBY, int KBY, int NKT>
-__global__ void __launch_bounds__(320, 1)
+__global__ void __launch_bounds__(384, 1)
 attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
   using C = Attn2Cfg<HD, BX, QBY, KBY, NKT>;
   constexpr int NATOM = C::NATOM, SN = C::SN, KR = C::KR, QR = C::QR, ST = C::KV_STAGES;
@@ -61,7 +88,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sQ = smem;                                   // [2 tiles][NATOM atoms][128 rows x 128 B]
   uint8_t* sK = sQ + 2 * C::Q_TILE_BYTES;
   uint8_t* sV = sK + ST * C::KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + ST * C::KV_BYTES);
+  uint8_t* sE = sV + ST * C::KV_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + C::E_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* k_full = bars + 2;        // [2]
@@ -72,14 +100,28 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* p_full = bars + 12;       // [2] per warpgroup, 128 arrivals
   uint64_t* o_full = bars + 14;       // [2] per warpgroup: last PV of the unit done
   uint64_t* o_free = bars + 16;       // [2] per warpgroup, 128 arrivals: O has been read, S/O region reusable
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  uint64_t* r_full = bars + 18;       // [2] per warpgroup, 128 arrivals: this unit's R operand is in TMEM
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int num_units = p.num_qtiles * p.heads;         // num_qtiles = query-tile PAIRS here
 
-  for (int i = threadIdx.x; i < (2 * C::Q_TILE_BYTES + 2 * ST * C::KV_BYTES) / 16; i += blockDim.x)
+  for (int i = threadIdx.x; i < (2 * C::Q_TILE_BYTES + 2 * ST * C::KV_BYTES + C::E_BYTES) / 16; i += blockDim.x)
     reinterpret_cast<uint4*>(smem)[i] = make_uint4(0, 0, 0, 0);
+  __syncthreads();
+  // one-hot selector E (K-major SW128 rows of 64 fp16): constant for the whole kernel
+  for (int k = threadIdx.x; k < KR; k += blockDim.x) {
+    const __half one = __float2half_rn(1.0f);
+    if (NKT > 1) {
+      const int c = k % 64;
+      *reinterpret_cast<__half*>(sE + sw128_offset(k, c >> 3) + (c & 7) * 2) = one;
+    } else {
+      const int c0 = k / BX, c1 = KBY + k % BX;
+      *reinterpret_cast<__half*>(sE + sw128_offset(k, c0 >> 3) + (c0 & 7) * 2) = one;
+      *reinterpret_cast<__half*>(sE + sw128_offset(k, c1 >> 3) + (c1 & 7) * 2) = one;
+    }
+  }
   fence_proxy_async_smem();
 
   if (warp == 0 && lane == 0) {
@@ -98,14 +140,19 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&p_full[i], 128);
       mbar_init(&o_full[i], 1);
       mbar_init(&o_free[i], 128);
+      mbar_init(&r_full[i], 128);
     }
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<512>(tmem_slot);
+  if (warp == 2) tmem_alloc<512>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // register re-allocation between warpgroups: the control warpgroup (TMA / MMA issue) keeps 96 registers per thread,
+  // the two softmax warpgroups get 200 (128*96 + 256*200 = 63488 <= 384*168, the pool the CTA was launched with)
+  if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
 
   auto unit_coords = [&](int unit, int& head, int& qy0, int& qy1, int& x0, int& ky0) {
     head = unit % p.heads;
@@ -127,10 +174,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
       uint32_t qph = 0, kst = 0, kph = 0, vst = 0, vph = 0;
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      int ui = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
         int head, qy0, qy1, x0, ky0;
         unit_coords(unit, head, qy0, qy1, x0, ky0);
+        attn_dbg(p, 64 * ui + 0);
         mbar_wait(q_empty, qph ^ 1);
+        attn_dbg(p, 64 * ui + 1);
         mbar_expect_tx(q_full, 2 * NATOM * QR * 128);
         for (int a = 0; a < NATOM; ++a) {
           tma_load_3d(sQ + a * 128 * 128, &tmQ, q_full, head * HD + a * 64, x0, qy0);
@@ -139,11 +189,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         qph ^= 1;
         for (int j = 0; j < NKT; ++j) {
           mbar_wait(&k_empty[kst], kph ^ 1);
+          if (j == 0) attn_dbg(p, 64 * ui + 2);
           mbar_expect_tx(&k_full[kst], NATOM * KR * 128);
           for (int a = 0; a < NATOM; ++a)
             tma_load_3d(sK + kst * C::KV_BYTES + a * C::KV_ATOM_BYTES, &tmKV, &k_full[kst], p.D + head * HD + a * 64, x0, ky0 + j * KBY);
           if (++kst == ST) { kst = 0; kph ^= 1; }
           mbar_wait(&v_empty[vst], vph ^ 1);
+          if (j == 0) attn_dbg(p, 64 * ui + 3);
           mbar_expect_tx(&v_full[vst], NATOM * KR * 128);
           for (int a = 0; a < NATOM; ++a)
             tma_load_3d(sV + vst * C::KV_BYTES + a * C::KV_ATOM_BYTES, &tmKV, &v_full[vst], 2 * p.D + head * HD + a * 64, x0, ky0 + j * KBY);
@@ -157,8 +209,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_s = umma_idesc_f16(128, SN, 0, 0);
       constexpr uint32_t idesc_o64 = umma_idesc_f16(128, 64, 0, 1);
       constexpr uint32_t idesc_o16 = umma_idesc_f16(128, 16, 0, 1);
-      uint32_t qph = 0, kst = 0, kph = 0, vst = 0, vph = 0, pph[2] = {0, 0}, fph[2] = {0, 0};
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV);
+      uint32_t qph = 0, kst = 0, kph = 0, vst = 0, vph = 0, pph[2] = {0, 0}, fph[2] = {0, 0}, rph = 0;
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aE = smem_u32(sE);
       auto issue_s = [&](int w) {                       // S_w = Q_w K^T into warpgroup w's columns
         const uint32_t d = tmem_base + uint32_t(w * 256);
 #pragma unroll
@@ -167,6 +219,10 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           const uint32_t b = aK + kst * C::KV_BYTES + (k / 4) * C::KV_ATOM_BYTES + (k % 4) * 32;
           tc_mma_f16(d, umma_desc_sw128(a), umma_desc_sw128(b), idesc_s, k != 0);
         }
+        // + rel-pos bias: S += R_w (TMEM, fp16) . E^T (one-hot, smem)
+#pragma unroll
+        for (int k = 0; k < C::RK / 16; ++k)
+          tc_mma_f16_ts(d, tmem_base + uint32_t(w * 256 + C::R_OFF + k * 8), umma_desc_sw128(aE + k * 32), idesc_s, 1u);
         tc_commit(&s_full[w]);
       };
       auto issue_pv = [&](int w, int j) {               // O_w (+)= P_w V_j, A = P from tensor memory
@@ -180,28 +236,37 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (NATOM == 2) tc_mma_f16_ts(d + 64, pa + uint32_t(k * 8), umma_desc_sw128(b + C::KV_ATOM_BYTES), idesc_o16, acc);
         }
       };
-      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+      int ui = 0;
+      for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
+        attn_dbg(p, 64 * ui + 8);
         mbar_wait(q_full, qph);
         qph ^= 1;
+        attn_dbg(p, 64 * ui + 9);
         mbar_wait(&k_full[kst], kph);
         tc_fence_after();
+        attn_dbg(p, 64 * ui + 10);
         for (int w = 0; w < 2; ++w) {                   // the warpgroup has read the previous unit's O (aliases S)
           mbar_wait(&o_free[w], fph[w] ^ 1);
           fph[w] ^= 1;
+          mbar_wait(&r_full[w], rph);                   // ... and has stored this unit's R operand
           tc_fence_after();
           issue_s(w);
+          attn_dbg(p, 64 * ui + 11 + w);
         }
+        rph ^= 1;
         tc_commit(&k_empty[kst]);
         if (++kst == ST) { kst = 0; kph ^= 1; }
         if (NKT == 1) tc_commit(q_empty);
         for (int j = 0; j < NKT; ++j) {
           const bool more = (j + 1 < NKT);
           mbar_wait(&v_full[vst], vph);
+          if (j == 0) attn_dbg(p, 64 * ui + 13);
           if (more) mbar_wait(&k_full[kst], kph);
           for (int w = 0; w < 2; ++w) {
             mbar_wait(&p_full[w], pph[w]);
             pph[w] ^= 1;
             tc_fence_after();
+            if (j == 0) attn_dbg(p, 64 * ui + 14 + w);
             issue_pv(w, j);
             if (!more) tc_commit(&o_full[w]);
             if (more) issue_s(w);                       // S_w of the next key tile overwrites the P it just consumed
@@ -216,60 +281,93 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         }
       }
     }
-  } else if (warp >= 2) {
-    // ------------------------------------------------------------ softmax warpgroups (warps 2-5 and 6-9)
-    const int w = (warp - 2) >> 2;                      // warpgroup = query tile
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ softmax warpgroups (warps 4-7 and 8-11)
+    const int w = (warp - 4) >> 2;                      // warpgroup = query tile
     const int q = warp & 3;
     const int r = q * 32 + lane;
     const uint32_t wg_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(w * 256);
     constexpr int NP = (BX == 64) ? 256 : 64;
     constexpr int SS = BX;
     uint32_t sph = 0, oph = 0;
-    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x) {
+    int ui = 0;
+    const bool tr = (r == 0);
+    for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
       int head, qy0, qy1, x0, ky0;
       unit_coords(unit, head, qy0, qy1, x0, ky0);
+      if (tr) attn_dbg(p, 64 * ui + 20 + 10 * w);
       const int qy = w ? qy1 : qy0;
       const int ty = qy + r / BX, tx = x0 + r % BX;
       const bool valid = (r < QR) && ty < 64 && tx < 64;
       const int token = ty * 64 + tx;
       const float* relrow = p.rel + (size_t(head) * 4096 + (valid ? token : 0)) * NP;
       const int qh = qy - ky0 + r / BX, qw = r % BX;
-      float relw[BX];
+      // this row's rel-pos terms -> packed fp16 operand R in tensor memory (divided by the score scale, because the
+      // accumulator is scaled afterwards: t = scale_log2e * (q.k + R.E))
+      {
+        const float inv_scale = 1.0f / p.scale_log2e;
+        uint32_t rk[C::RK / 2];
+        if (NKT > 1) {
 #pragma unroll
-      for (int i = 0; i < BX; ++i) relw[i] = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - i) : 0.f;
+          for (int i = 0; i < 32; ++i) {
+            const float a0 = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - 2 * i) * inv_scale : 0.f;
+            const float a1 = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - (2 * i + 1)) * inv_scale : 0.f;
+            __half2 h = __floats2half2_rn(a0, a1);
+            rk[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        } else {
+          float rv[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) rv[i] = 0.f;
+#pragma unroll
+          for (int i = 0; i < KBY; ++i) rv[i] = valid ? __ldg(relrow + qh + (SS - 1) - i) * inv_scale : 0.f;
+#pragma unroll
+          for (int i = 0; i < BX; ++i) rv[KBY + i] = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - i) * inv_scale : 0.f;
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            __half2 h = __floats2half2_rn(rv[2 * i], rv[2 * i + 1]);
+            rk[i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        }
+        if constexpr (C::RK == 64) tmem_st32(wg_addr + C::R_OFF, rk); else tmem_st16(wg_addr + C::R_OFF, rk);
+        tc_wait_st();
+        tc_fence_before();
+        mbar_arrive(&r_full[w]);
+      }
       float m_ref = 0.f, l_run = 0.f;
 
       for (int j = 0; j < NKT; ++j) {
-        float relh[KBY];
+        // global blocks: the two key rows of this tile share rel_h terms that stay scalar; windowed: all bias is in the MMA
+        constexpr int NG = (NKT > 1) ? KBY : 1;
+        float relh[NG];
 #pragma unroll
-        for (int i = 0; i < KBY; ++i) relh[i] = valid ? __ldg(relrow + qh + (SS - 1) - ((NKT == 1 ? 0 : j * KBY) + i)) : 0.f;
+        for (int i = 0; i < NG; ++i) relh[i] = (NKT > 1 && valid) ? __ldg(relrow + qh + (SS - 1) - (j * KBY + i)) : 0.f;
+        if (tr && j == 0) attn_dbg(p, 64 * ui + 21 + 10 * w);
         mbar_wait(&s_full[w], sph);
         sph ^= 1;
         tc_fence_after();
-        // pass 1: row max of the biased, scaled scores (log2 domain)
-        float m_tile = -INFINITY;
+        if (tr && j == 0) attn_dbg(p, 64 * ui + 22 + 10 * w);
+        // pass 1: row max (log2 domain).  The accumulator already holds q.k + bias/scale: one FMNMX per score, the
+        // scale (> 0) and the scalar rel_h term are applied to the group maxima
+        float m_g[NG];
+#pragma unroll
+        for (int i = 0; i < NG; ++i) m_g[i] = -INFINITY;
         static_for<0, SN, 32>([&](auto c0c) {
           constexpr int c0 = decltype(c0c)::value;
-          if constexpr (SN - c0 >= 32) {
-            uint32_t v[32];
-            tmem_ld32(wg_addr + c0, v);
-            tc_wait_ld();
+          constexpr int W = (SN - c0 >= 32) ? 32 : 16;
+          uint32_t v[W];
+          if constexpr (W == 32) tmem_ld32(wg_addr + c0, v); else tmem_ld16(wg_addr + c0, v);
+          tc_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              const int c = c0 + i;
-              if (c < KR) m_tile = fmaxf(m_tile, fmaf(__uint_as_float(v[i]), p.scale_log2e, relh[c / BX] + relw[c % BX]));
-            }
-          } else {
-            uint32_t v[16];
-            tmem_ld16(wg_addr + c0, v);
-            tc_wait_ld();
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-              const int c = c0 + i;
-              if (c < KR) m_tile = fmaxf(m_tile, fmaf(__uint_as_float(v[i]), p.scale_log2e, relh[c / BX] + relw[c % BX]));
-            }
+          for (int i = 0; i < W; ++i) {
+            const int c = c0 + i;
+            if (c < KR) m_g[NKT > 1 ? c / BX : 0] = fmaxf(m_g[NKT > 1 ? c / BX : 0], __uint_as_float(v[i]));
           }
         });
+        float m_tile = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < NG; ++i) m_tile = fmaxf(m_tile, fmaf(m_g[i], p.scale_log2e, relh[i]));
+        if (tr && j == 0) attn_dbg(p, 64 * ui + 23 + 10 * w);
         if (j == 0) {
           m_ref = m_tile;
         } else {
@@ -300,57 +398,41 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             m_ref = m_new;
           }
         }
-        // (opaque no-op: keeps the compiler from carrying all KR precomputed bias sums of pass 1 into pass 2, which
-        //  costs ~120 spilled registers; recomputing relh + relw is one FADD)
+        // pass 2: P = exp2(scale * acc + rel_h - m_ref) -> fp16 pairs -> tensor memory (over the first half of S)
+        float dh[NG];
 #pragma unroll
-        for (int i = 0; i < BX; ++i) asm volatile("" : "+f"(relw[i]));
-        // pass 2: P = exp2(s - m_ref) -> fp16 pairs -> tensor memory (over the first half of this row's S columns)
+        for (int i = 0; i < NG; ++i) dh[i] = relh[i] - m_ref;
         float l_tile = 0.f;
         static_for<0, SN, 32>([&](auto c0c) {
           constexpr int c0 = decltype(c0c)::value;
-          if constexpr (SN - c0 >= 32) {
-            uint32_t v[32];
-            tmem_ld32(wg_addr + c0, v);
-            tc_wait_ld();
-            uint32_t pk[16];
-#pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              float e0 = 0.f, e1 = 0.f;
-              const int c = c0 + i;
-              if (c < KR) e0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, relh[c / BX] + relw[c % BX]) - m_ref);
-              if (c + 1 < KR) e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, relh[(c + 1) / BX] + relw[(c + 1) % BX]) - m_ref);
-              l_tile += e0 + e1;
-              __half2 h = __floats2half2_rn(e0, e1);
-              pk[i / 2] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            tmem_st16(wg_addr + c0 / 2, pk);
-          } else {
-            uint32_t v[16];
-            tmem_ld16(wg_addr + c0, v);
-            tc_wait_ld();
-            uint32_t pk[8];
-#pragma unroll
-            for (int i = 0; i < 16; i += 2) {
-              float e0 = 0.f, e1 = 0.f;
-              const int c = c0 + i;
-              if (c < KR) e0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2e, relh[c / BX] + relw[c % BX]) - m_ref);
-              if (c + 1 < KR) e1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, relh[(c + 1) / BX] + relw[(c + 1) % BX]) - m_ref);
-              l_tile += e0 + e1;
-              __half2 h = __floats2half2_rn(e0, e1);
-              pk[i / 2] = *reinterpret_cast<uint32_t*>(&h);
-            }
-            tmem_st8(wg_addr + c0 / 2, pk);
-          }
+          constexpr int W = (SN - c0 >= 32) ? 32 : 16;
+          uint32_t v[W];
+          if constexpr (W == 32) tmem_ld32(wg_addr + c0, v); else tmem_ld16(wg_addr + c0, v);
+          tc_wait_ld();
+          uint32_t pk[W / 2];
+          static_for<0, W, 2>([&](auto ic) {
+            constexpr int i = decltype(ic)::value;
+            constexpr int c = c0 + i;
+            float e0 = 0.f, e1 = 0.f;
+            if constexpr (c < KR) e0 = ex2_mixed<i>(fmaf(__uint_as_float(v[i]), p.scale_log2e, dh[NKT > 1 ? c / BX : 0]));
+            if constexpr (c + 1 < KR) e1 = ex2_mixed<i + 1>(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, dh[NKT > 1 ? (c + 1) / BX : 0]));
+            l_tile += e0 + e1;
+            __half2 h = __floats2half2_rn(e0, e1);
+            pk[i / 2] = *reinterpret_cast<uint32_t*>(&h);
+          });
+          if constexpr (W == 32) tmem_st16(wg_addr + c0 / 2, pk); else tmem_st8(wg_addr + c0 / 2, pk);
         });
         l_run += l_tile;
         tc_wait_st();
         tc_fence_before();
         mbar_arrive(&p_full[w]);
+        if (tr && j == 0) attn_dbg(p, 64 * ui + 24 + 10 * w);
       }
       // O complete: normalise and write the fp16 output row
       mbar_wait(&o_full[w], oph);
       oph ^= 1;
       tc_fence_after();
+      if (tr) attn_dbg(p, 64 * ui + 25 + 10 * w);
       const float inv = 1.0f / l_run;
       __half* o = p.out + size_t(valid ? token : 0) * p.D + head * HD;
       static_for<0, HD, 32>([&](auto c0c) {
@@ -393,12 +475,13 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       });
       tc_fence_before();
       mbar_arrive(&o_free[w]);
+      if (tr) attn_dbg(p, 64 * ui + 26 + 10 * w);
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) {
+  if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }

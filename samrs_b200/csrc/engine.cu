@@ -113,6 +113,30 @@ static int launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const 
   return 0;
 }
 
+// cluster-multicast variant (CM = 2): launched with a (2,1,1) cluster
+template <int BN, bool OH, int ACT>
+static int launch_gemm_mc_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    SAMRS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OH, ACT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_done = true;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(GEMM_THREADS);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  SAMRS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<BN, OH, ACT, 2>, tA, tB, tC, p));
+  count_launch();
+  return 0;
+}
+
 template <int BN, bool OH, int ACT>
 static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
@@ -141,13 +165,17 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   if (p.batch < 1) p.batch = 1;
   p.a_rank3 = a_map_rank3 ? 1 : 0;
   if (p.K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) SAMRS_FAIL("gemm: K and leading dimensions must be multiples of 8");
-  // force_bn: 0 = choose; 128/160/256 = 1-CTA kernel with that N tile; 1128/1160/1256 = CTA-pair kernel
+  // force_bn: 0 = choose; 128/160/224/256 = 1-CTA kernel with that N tile; 1000 + bn = CTA-pair kernel;
+  // 2000 + bn = cluster of two 1-CTA tiles sharing B through TMA multicast
   int bn = force_bn % 1000;
-  bool pair = force_bn >= 1000;
+  bool pair = force_bn >= 1000 && force_bn < 2000;
+  bool mcast = force_bn >= 2000;
   if (force_bn == 0 && p.M == 4096 && p.batch == 1 && (p.N == 1280 || p.N == 3840 || p.N == 5120) && num_sms == 148) {
     // ViT-H shapes: measured best configurations (profiles/r01_gemm_sweep_v3.json)
     bn = (p.N == 1280) ? 160 : (p.N == 3840 ? 224 : 256);
     pair = false;
+    static const bool use_mcast = getenv("SAMRS_GEMM_MCAST") != nullptr;
+    mcast = use_mcast;
   } else if (force_bn == 0) {
     // pick the (kernel, N tile) with the smallest modelled duration = waves x per-tile time
     const int cands[4] = {256, 224, 160, 128};
@@ -170,7 +198,8 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   CUtensorMap tA, tB;
   if (a_map_rank3) tA = *a_map_rank3;
   else SAMRS_TRY(make_tmap_2d(&tA, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, GEMM_BK, GEMM_BM));
-  SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t(pair ? bn / 2 : bn)));
+  if (mcast && (((p.M + 127) / 128) % 2 != 0 || (num_sms & 1) || a_map_rank3)) mcast = false;
+  SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t((pair || mcast) ? bn / 2 : bn)));
   CUtensorMap tC;
   SAMRS_TRY(make_tmap_out(&tC, p.out, out_half, uint64_t(p.N), uint64_t(p.M), uint64_t(p.batch), uint64_t(p.ldc), uint64_t(p.out_batch_stride)));
   if (p.res != nullptr && (p.ldr % 4 != 0)) SAMRS_FAIL("gemm: residual leading dimension must be a multiple of 4");
@@ -191,6 +220,21 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
     SAMRS_GEMM2_CASE(128)
 #undef SAMRS_GEMM2_CASE
     SAMRS_FAIL("gemm: unsupported N tile");
+  }
+  if (mcast) {
+    const int gridm = (tiles < num_sms ? tiles : num_sms) & ~1;
+#define SAMRS_GEMMMC_CASE(BN_)                                                                        \
+  if (bn == BN_) {                                                                                  \
+    if (out_half && act == 0) return launch_gemm_mc_inst<BN_, true, 0>(tA, tB, tC, p, gridm, stream);   \
+    if (out_half && act == 1) return launch_gemm_mc_inst<BN_, true, 1>(tA, tB, tC, p, gridm, stream);   \
+    if (!out_half && act == 0) return launch_gemm_mc_inst<BN_, false, 0>(tA, tB, tC, p, gridm, stream); \
+    SAMRS_FAIL("gemm: unsupported epilogue");                                                       \
+  }
+    SAMRS_GEMMMC_CASE(256)
+    SAMRS_GEMMMC_CASE(224)
+    SAMRS_GEMMMC_CASE(160)
+#undef SAMRS_GEMMMC_CASE
+    SAMRS_FAIL("gemm: unsupported N tile for the multicast kernel");
   }
   const int grid = tiles < num_sms ? tiles : num_sms;
 #define SAMRS_GEMM_CASE(BN_)                                                                        \
@@ -312,6 +356,7 @@ static int set_err(Engine* e, int rc) {
   return rc;
 }
 
+static void* g_attn_dbg = nullptr;            // device buffer for attention pipeline traces (tools only)
 // ------------------------------------------------------------------ small launch helpers
 static float* g_splitk_ws = nullptr;          // split-K workspace of the active engine (set by LaunchScope)
 static size_t g_splitk_ws_floats = 0;
@@ -385,7 +430,7 @@ static int launch_attn2_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, cons
   }
   const int units = p.num_qtiles * p.heads;
   const int grid = units < num_sms ? units : num_sms;
-  attn_tc2_kernel<HD, BX, QBY, KBY, NKT><<<grid, 320, C::kSmemBytes, st>>>(tQ, tKV, p);
+  attn_tc2_kernel<HD, BX, QBY, KBY, NKT><<<grid, 384, C::kSmemBytes, st>>>(tQ, tKV, p);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -414,6 +459,7 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
   p.D = D;
   p.heads = e->heads;
   p.scale_log2e = (1.0f / sqrtf(float(hd))) * 1.4426950408889634f;
+  p.dbg = static_cast<unsigned long long*>(g_attn_dbg);
   CUtensorMap tQ, tKV;
   const uint64_t pitch_x = uint64_t(3 * D) * 2, pitch_y = pitch_x * 64;
   static const bool attn_v1 = getenv("SAMRS_ATTN_V1") != nullptr;     // first-generation kernel (one query tile per CTA)
@@ -997,6 +1043,7 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
 using namespace samrs;
 static void* g_gemm_dbg = nullptr;      // device buffer of 4096 u64 for gemm pipeline traces (tests/tools only)
 extern "C" void samrs_test_set_gemm_trace(void* dev_buf) { g_gemm_dbg = dev_buf; }
+extern "C" void samrs_test_set_attn_trace(void* dev_buf) { samrs::g_attn_dbg = dev_buf; }
 
 struct LaunchScope {
   explicit LaunchScope(Engine* e) {

@@ -155,7 +155,10 @@ __device__ __forceinline__ void gemm_load_bias(const GemmParams& p, int n0, int 
   }
 }
 
-template <int BN, bool OUT_HALF, int ACT>
+// CM = 2: two CTAs of a cluster work on vertically adjacent tiles (2m, n) / (2m+1, n) and share the B tile: each loads
+// half of it and TMA-multicasts the half into both CTAs' shared memory, which cuts the L2->SM bytes per flop from
+// (128 + BN) to (128 + BN/2) per k-block and moves the main loop from feed-bound (~80 B/clk/SM) to MMA-bound.
+template <int BN, bool OUT_HALF, int ACT, int CM = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
@@ -176,6 +179,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
   const int tiles_mn = p.tiles_m * p.tiles_n;
   const int num_tiles = tiles_mn * p.batch;
+  // CM == 2: `unit` = pair of M tiles; tile index of this CTA = 2 * (unit's m-pair) + rank, same n
+  const int crank = (CM == 2) ? int(cluster_ctarank()) : 0;
+  const int first = (CM == 2) ? int(blockIdx.x >> 1) : int(blockIdx.x);
+  const int stride = (CM == 2) ? int(gridDim.x >> 1) : int(gridDim.x);
+  const int num_units = (CM == 2) ? num_tiles / 2 : num_tiles;
+  auto unit_to_tile = [&](int u) { return (CM == 2) ? ((u % (p.tiles_m / 2)) * 2 + crank + (u / (p.tiles_m / 2)) * p.tiles_m) : u; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -185,7 +194,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < S; ++i) {
       mbar_init(&full[i], 1);
-      mbar_init(&empty[i], 1);
+      mbar_init(&empty[i], CM);          // CM == 2: both CTAs' MMAs must have released the stage (the peer writes into it)
     }
     mbar_init(&tfull[0], 1);
     mbar_init(&tfull[1], 1);
@@ -195,7 +204,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 2) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   tc_fence_before();
-  __syncthreads();
+  if (CM == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -204,7 +213,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int u = first; u < num_units; u += stride) {
+        const int t = unit_to_tile(u);
         const int bt = t / tiles_mn, tt = t % tiles_mn;
         const int m0 = (tt % p.tiles_m) * GEMM_BM;
         const int n0 = (tt / p.tiles_m) * BN;
@@ -215,7 +225,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_expect_tx(&full[stage], Cfg::kStageBytes);
           if (p.a_rank3) tma_load_3d(sa, &tmA, &full[stage], kb * GEMM_BK, bt, m0);
           else tma_load_2d(sa, &tmA, &full[stage], kb * GEMM_BK, m0);
-          tma_load_2d(sb, &tmB, &full[stage], kb * GEMM_BK, n0);
+          if (CM == 2) tma_load_2d_mcast(sb + crank * (BN / 2) * 128, &tmB, &full[stage], kb * GEMM_BK, n0 + crank * (BN / 2), 0x3);
+          else tma_load_2d(sb, &tmB, &full[stage], kb * GEMM_BK, n0);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
@@ -228,7 +239,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+      for (int u = first; u < num_units; u += stride) {
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
@@ -244,7 +255,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // advance 16 fp16 (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
             tc_mma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
           }
-          tc_commit(&empty[stage]);
+          if (CM == 2) tc_commit_mcast(&empty[stage], 0x3); else tc_commit(&empty[stage]);
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
         tc_commit(&tfull[as]);
@@ -261,7 +272,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int cb = (warp < 8) ? 0 : SPLIT, ce = (warp < 8) ? SPLIT : NCH;
     int as = 0;
     uint32_t aphase = 0;
-    for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+    for (int u = first; u < num_units; u += stride) {
+      const int t = unit_to_tile(u);
       const int bt = t / tiles_mn, tt = t % tiles_mn;
       const int m0 = (tt % p.tiles_m) * GEMM_BM;
       const int n0 = (tt / p.tiles_m) * BN;
@@ -282,7 +294,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CM == 2) cluster_sync_all(); else __syncthreads();     // the peer may still multicast into / signal this CTA
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);

@@ -7,7 +7,7 @@ from samrs_b200.engine import Engine
 eng = Engine("vit_t64", "cuda:0")
 shapes = {"qkv": (4096, 3840, 1280, True, False), "proj": (4096, 1280, 1280, False, False),
           "lin1": (4096, 5120, 1280, True, True), "lin2": (4096, 1280, 5120, False, False)}
-cfgs = [int(c) for c in sys.argv[1:]] or [160, 224, 256, 1160, 1224, 1256]
+cfgs = [int(c) for c in sys.argv[1:]] or [160, 224, 256, 2160, 2224, 2256]
 res = {}
 for name, (M, N, K, half, gelu) in shapes.items():
     A = (torch.randn(M, K, device="cuda") * 1.0).half()
