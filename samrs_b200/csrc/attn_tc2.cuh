@@ -61,7 +61,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 
 // exp2 on the FMA / integer pipes (Cody-Waite split + degree-4 polynomial on [-0.5, 0.5], relative error 3.6e-6, far
 // below the fp16 rounding of P).  The MUFU unit retires one warp-wide ex2 per 8 clocks per SM sub-partition and the
-// softmax warps were bound by it (and by the fp32->fp16 packs that share it): every third exponential goes here.
+// windowed softmax was bound by it (and by the fp32->fp16 packs that share it): every third exponential of the
+// windowed kernel goes here (the global kernel measured slightly slower with it and keeps MUFU only).
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -125.0f);
   const float r = x + 12582912.0f;                 // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
@@ -72,9 +73,9 @@ __device__ __forceinline__ float ex2_poly(float x) {
   q = fmaf(q, f, 1.0000001f);
   return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
 }
-template <int I>
+template <int I, bool POLY>
 __device__ __forceinline__ float ex2_mixed(float x) {
-  if constexpr (false && I % 3 == 2) return ex2_poly(x);   // measured: no gain (the global kernel is issue-bound), kept for reference
+  if constexpr (POLY && I % 3 == 2) return ex2_poly(x);
   else return ex2_approx(x);
 }
 
@@ -172,7 +173,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // warp-uniform loop, one elected lane issues (a divergent `lane == 0` branch makes the compiler wrap every TMA / MMA
+    // instruction in an R2UR.BROADCAST waterfall loop)
+    {
       uint32_t qph = 0, kst = 0, kph = 0, vst = 0, vph = 0;
       int ui = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
@@ -181,31 +184,43 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         attn_dbg(p, 64 * ui + 0);
         mbar_wait(q_empty, qph ^ 1);
         attn_dbg(p, 64 * ui + 1);
-        mbar_expect_tx(q_full, 2 * NATOM * QR * 128);
-        for (int a = 0; a < NATOM; ++a) {
-          tma_load_3d(sQ + a * 128 * 128, &tmQ, q_full, head * HD + a * 64, x0, qy0);
-          tma_load_3d(sQ + C::Q_TILE_BYTES + a * 128 * 128, &tmQ, q_full, head * HD + a * 64, x0, qy1);
+        if (elect_one()) {
+          mbar_expect_tx(q_full, 2 * NATOM * QR * 128);
+#pragma unroll
+          for (int a = 0; a < NATOM; ++a) {
+            tma_load_3d(sQ + a * 128 * 128, &tmQ, q_full, head * HD + a * 64, x0, qy0);
+            tma_load_3d(sQ + C::Q_TILE_BYTES + a * 128 * 128, &tmQ, q_full, head * HD + a * 64, x0, qy1);
+          }
         }
+        __syncwarp();
         qph ^= 1;
         for (int j = 0; j < NKT; ++j) {
           mbar_wait(&k_empty[kst], kph ^ 1);
           if (j == 0) attn_dbg(p, 64 * ui + 2);
-          mbar_expect_tx(&k_full[kst], NATOM * KR * 128);
-          for (int a = 0; a < NATOM; ++a)
-            tma_load_3d(sK + kst * C::KV_BYTES + a * C::KV_ATOM_BYTES, &tmKV, &k_full[kst], p.D + head * HD + a * 64, x0, ky0 + j * KBY);
+          if (elect_one()) {
+            mbar_expect_tx(&k_full[kst], NATOM * KR * 128);
+#pragma unroll
+            for (int a = 0; a < NATOM; ++a)
+              tma_load_3d(sK + kst * C::KV_BYTES + a * C::KV_ATOM_BYTES, &tmKV, &k_full[kst], p.D + head * HD + a * 64, x0, ky0 + j * KBY);
+          }
+          __syncwarp();
           if (++kst == ST) { kst = 0; kph ^= 1; }
           mbar_wait(&v_empty[vst], vph ^ 1);
           if (j == 0) attn_dbg(p, 64 * ui + 3);
-          mbar_expect_tx(&v_full[vst], NATOM * KR * 128);
-          for (int a = 0; a < NATOM; ++a)
-            tma_load_3d(sV + vst * C::KV_BYTES + a * C::KV_ATOM_BYTES, &tmKV, &v_full[vst], 2 * p.D + head * HD + a * 64, x0, ky0 + j * KBY);
+          if (elect_one()) {
+            mbar_expect_tx(&v_full[vst], NATOM * KR * 128);
+#pragma unroll
+            for (int a = 0; a < NATOM; ++a)
+              tma_load_3d(sV + vst * C::KV_BYTES + a * C::KV_ATOM_BYTES, &tmKV, &v_full[vst], 2 * p.D + head * HD + a * 64, x0, ky0 + j * KBY);
+          }
+          __syncwarp();
           if (++vst == ST) { vst = 0; vph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    {
       constexpr uint32_t idesc_s = umma_idesc_f16(128, SN, 0, 0);
       constexpr uint32_t idesc_o64 = umma_idesc_f16(128, 64, 0, 1);
       constexpr uint32_t idesc_o16 = umma_idesc_f16(128, 16, 0, 1);
@@ -213,28 +228,34 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aE = smem_u32(sE);
       auto issue_s = [&](int w) {                       // S_w = Q_w K^T into warpgroup w's columns
         const uint32_t d = tmem_base + uint32_t(w * 256);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k) {
-          const uint32_t a = aQ + w * C::Q_TILE_BYTES + (k / 4) * (128 * 128) + (k % 4) * 32;
-          const uint32_t b = aK + kst * C::KV_BYTES + (k / 4) * C::KV_ATOM_BYTES + (k % 4) * 32;
-          tc_mma_f16(d, umma_desc_sw128(a), umma_desc_sw128(b), idesc_s, k != 0);
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint32_t a = aQ + w * C::Q_TILE_BYTES + (k / 4) * (128 * 128) + (k % 4) * 32;
+            const uint32_t b = aK + kst * C::KV_BYTES + (k / 4) * C::KV_ATOM_BYTES + (k % 4) * 32;
+            tc_mma_f16(d, umma_desc_sw128(a), umma_desc_sw128(b), idesc_s, k != 0);
+          }
+          // + rel-pos bias: S += R_w (TMEM, fp16) . E^T (one-hot, smem)
+#pragma unroll
+          for (int k = 0; k < C::RK / 16; ++k)
+            tc_mma_f16_ts(d, tmem_base + uint32_t(w * 256 + C::R_OFF + k * 8), umma_desc_sw128(aE + k * 32), idesc_s, 1u);
+          tc_commit(&s_full[w]);
         }
-        // + rel-pos bias: S += R_w (TMEM, fp16) . E^T (one-hot, smem)
-#pragma unroll
-        for (int k = 0; k < C::RK / 16; ++k)
-          tc_mma_f16_ts(d, tmem_base + uint32_t(w * 256 + C::R_OFF + k * 8), umma_desc_sw128(aE + k * 32), idesc_s, 1u);
-        tc_commit(&s_full[w]);
+        __syncwarp();
       };
       auto issue_pv = [&](int w, int j) {               // O_w (+)= P_w V_j, A = P from tensor memory
         const uint32_t d = tmem_base + uint32_t(w * 256 + C::O_OFF);
         const uint32_t pa = tmem_base + uint32_t(w * 256);
+        if (elect_one()) {
 #pragma unroll
-        for (int k = 0; k < SN / 16; ++k) {
-          const uint32_t b = aV + vst * C::KV_BYTES + k * 2048;
-          const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
-          tc_mma_f16_ts(d, pa + uint32_t(k * 8), umma_desc_sw128(b), idesc_o64, acc);
-          if (NATOM == 2) tc_mma_f16_ts(d + 64, pa + uint32_t(k * 8), umma_desc_sw128(b + C::KV_ATOM_BYTES), idesc_o16, acc);
+          for (int k = 0; k < SN / 16; ++k) {
+            const uint32_t b = aV + vst * C::KV_BYTES + k * 2048;
+            const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
+            tc_mma_f16_ts(d, pa + uint32_t(k * 8), umma_desc_sw128(b), idesc_o64, acc);
+            if (NATOM == 2) tc_mma_f16_ts(d + 64, pa + uint32_t(k * 8), umma_desc_sw128(b + C::KV_ATOM_BYTES), idesc_o16, acc);
+          }
         }
+        __syncwarp();
       };
       int ui = 0;
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
@@ -254,9 +275,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           attn_dbg(p, 64 * ui + 11 + w);
         }
         rph ^= 1;
-        tc_commit(&k_empty[kst]);
+        if (elect_one()) tc_commit(&k_empty[kst]);
         if (++kst == ST) { kst = 0; kph ^= 1; }
-        if (NKT == 1) tc_commit(q_empty);
+        if ((NKT == 1) && elect_one()) tc_commit(q_empty);
         for (int j = 0; j < NKT; ++j) {
           const bool more = (j + 1 < NKT);
           mbar_wait(&v_full[vst], vph);
@@ -268,15 +289,15 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             tc_fence_after();
             if (j == 0) attn_dbg(p, 64 * ui + 14 + w);
             issue_pv(w, j);
-            if (!more) tc_commit(&o_full[w]);
+            if ((!more) && elect_one()) tc_commit(&o_full[w]);
             if (more) issue_s(w);                       // S_w of the next key tile overwrites the P it just consumed
           }
-          tc_commit(&v_empty[vst]);
+          if (elect_one()) tc_commit(&v_empty[vst]);
           if (++vst == ST) { vst = 0; vph ^= 1; }
           if (more) {
-            tc_commit(&k_empty[kst]);
+            if (elect_one()) tc_commit(&k_empty[kst]);
             if (++kst == ST) { kst = 0; kph ^= 1; }
-            if (j + 2 == NKT) tc_commit(q_empty);
+            if ((j + 2 == NKT) && elect_one()) tc_commit(q_empty);
           }
         }
       }
@@ -292,6 +313,42 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     uint32_t sph = 0, oph = 0;
     int ui = 0;
     const bool tr = (r == 0);
+    // rel-pos terms of this thread's query row for unit `un`, divided by the score scale (the accumulator is scaled
+    // afterwards: t = scale_log2e * (q.k + R.E)) and packed to fp16 pairs = one row of the TMEM operand R
+    uint32_t rk_next[C::RK / 2];
+    auto load_rk = [&](int un) {
+      int head, qy0, qy1, x0, ky0;
+      unit_coords(un, head, qy0, qy1, x0, ky0);
+      const int qy = w ? qy1 : qy0;
+      const int ty = qy + r / BX, tx = x0 + r % BX;
+      const bool valid = (r < QR) && ty < 64 && tx < 64;
+      const float* relrow = p.rel + (size_t(head) * 4096 + (valid ? ty * 64 + tx : 0)) * NP;
+      const int qh = qy - ky0 + r / BX, qw = r % BX;
+      const float inv_scale = 1.0f / p.scale_log2e;
+      if (NKT > 1) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const float a0 = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - 2 * i) * inv_scale : 0.f;
+          const float a1 = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - (2 * i + 1)) * inv_scale : 0.f;
+          __half2 h = __floats2half2_rn(a0, a1);
+          rk_next[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      } else {
+        float rv[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) rv[i] = 0.f;
+#pragma unroll
+        for (int i = 0; i < KBY; ++i) rv[i] = valid ? __ldg(relrow + qh + (SS - 1) - i) * inv_scale : 0.f;
+#pragma unroll
+        for (int i = 0; i < BX; ++i) rv[KBY + i] = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - i) * inv_scale : 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          __half2 h = __floats2half2_rn(rv[2 * i], rv[2 * i + 1]);
+          rk_next[i] = *reinterpret_cast<uint32_t*>(&h);
+        }
+      }
+    };
+    if (int(blockIdx.x) < num_units) load_rk(blockIdx.x);
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
       int head, qy0, qy1, x0, ky0;
       unit_coords(unit, head, qy0, qy1, x0, ky0);
@@ -302,38 +359,11 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int token = ty * 64 + tx;
       const float* relrow = p.rel + (size_t(head) * 4096 + (valid ? token : 0)) * NP;
       const int qh = qy - ky0 + r / BX, qw = r % BX;
-      // this row's rel-pos terms -> packed fp16 operand R in tensor memory (divided by the score scale, because the
-      // accumulator is scaled afterwards: t = scale_log2e * (q.k + R.E))
-      {
-        const float inv_scale = 1.0f / p.scale_log2e;
-        uint32_t rk[C::RK / 2];
-        if (NKT > 1) {
-#pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float a0 = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - 2 * i) * inv_scale : 0.f;
-            const float a1 = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - (2 * i + 1)) * inv_scale : 0.f;
-            __half2 h = __floats2half2_rn(a0, a1);
-            rk[i] = *reinterpret_cast<uint32_t*>(&h);
-          }
-        } else {
-          float rv[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) rv[i] = 0.f;
-#pragma unroll
-          for (int i = 0; i < KBY; ++i) rv[i] = valid ? __ldg(relrow + qh + (SS - 1) - i) * inv_scale : 0.f;
-#pragma unroll
-          for (int i = 0; i < BX; ++i) rv[KBY + i] = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - i) * inv_scale : 0.f;
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            __half2 h = __floats2half2_rn(rv[2 * i], rv[2 * i + 1]);
-            rk[i] = *reinterpret_cast<uint32_t*>(&h);
-          }
-        }
-        if constexpr (C::RK == 64) tmem_st32(wg_addr + C::R_OFF, rk); else tmem_st16(wg_addr + C::R_OFF, rk);
-        tc_wait_st();
-        tc_fence_before();
-        mbar_arrive(&r_full[w]);
-      }
+      // this row's packed rel-pos operand R was prefetched during the previous unit (rk_next): store it to tensor memory
+      if constexpr (C::RK == 64) tmem_st32(wg_addr + C::R_OFF, rk_next); else tmem_st16(wg_addr + C::R_OFF, rk_next);
+      tc_wait_st();
+      tc_fence_before();
+      mbar_arrive(&r_full[w]);
       float m_ref = 0.f, l_run = 0.f;
 
       for (int j = 0; j < NKT; ++j) {
@@ -414,8 +444,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             constexpr int i = decltype(ic)::value;
             constexpr int c = c0 + i;
             float e0 = 0.f, e1 = 0.f;
-            if constexpr (c < KR) e0 = ex2_mixed<i>(fmaf(__uint_as_float(v[i]), p.scale_log2e, dh[NKT > 1 ? c / BX : 0]));
-            if constexpr (c + 1 < KR) e1 = ex2_mixed<i + 1>(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, dh[NKT > 1 ? (c + 1) / BX : 0]));
+            if constexpr (c < KR) e0 = ex2_mixed<i, NKT == 1>(fmaf(__uint_as_float(v[i]), p.scale_log2e, dh[NKT > 1 ? c / BX : 0]));
+            if constexpr (c + 1 < KR) e1 = ex2_mixed<i + 1, NKT == 1>(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, dh[NKT > 1 ? (c + 1) / BX : 0]));
             l_tile += e0 + e1;
             __half2 h = __floats2half2_rn(e0, e1);
             pk[i / 2] = *reinterpret_cast<uint32_t*>(&h);
@@ -428,6 +458,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive(&p_full[w]);
         if (tr && j == 0) attn_dbg(p, 64 * ui + 24 + 10 * w);
       }
+      if (unit + int(gridDim.x) < num_units) load_rk(unit + gridDim.x);    // prefetch the next unit's R while PV runs
       // O complete: normalise and write the fp16 output row
       mbar_wait(&o_full[w], oph);
       oph ^= 1;

@@ -41,7 +41,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (done) return;
-    if (it > (1u << 26)) {
+    if (it > (1u << 22)) {   // ~10 s of polling: far beyond any legitimate wait
       printf("samrs: mbarrier watchdog block %d thread %d bar %u parity %u\n", blockIdx.x, threadIdx.x, addr, parity);
       __trap();
     }

@@ -173,6 +173,14 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   if (force_bn == 0 && p.M == 4096 && p.batch == 1 && (p.N == 1280 || p.N == 3840 || p.N == 5120) && num_sms == 148) {
     // ViT-H shapes: measured best configurations (profiles/r01_gemm_sweep_v3.json)
     bn = (p.N == 1280) ? 160 : (p.N == 3840 ? 224 : 256);
+    // experiment hook: SAMRS_BN="n1280,n3840,n5120" (e.g. "256,256,256") overrides the table
+    static int env_bn[3] = {-1, 0, 0};
+    if (env_bn[0] < 0) {
+      env_bn[0] = 0;
+      if (const char* s = getenv("SAMRS_BN")) sscanf(s, "%d,%d,%d", &env_bn[0], &env_bn[1], &env_bn[2]);
+    }
+    const int ov = env_bn[p.N == 1280 ? 0 : (p.N == 3840 ? 1 : 2)];
+    if (ov > 0) bn = ov;
     pair = false;
     static const bool use_mcast = getenv("SAMRS_GEMM_MCAST") != nullptr;
     mcast = use_mcast;
@@ -449,7 +457,7 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
     SAMRS_TRY(make_tmap_3d(&tA, qkv, uint64_t(hd), uint64_t(e->heads), 4096, uint64_t(hd) * 2, uint64_t(3 * D) * 2, GEMM_BK, 1, GEMM_BM));
     GemmParams gp;
     gp.M = 4096; gp.N = NP; gp.K = hd; gp.out = e->rel; gp.ldc = NP; gp.bias = nullptr; gp.res = nullptr; gp.ldr = 0; gp.res_mod = 0;
-    gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f; gp.dbg = nullptr; gp.accumulate = 0;
+    gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f; gp.dbg = nullptr; gp.dbg_mode = 0; gp.accumulate = 0;
     SAMRS_TRY(launch_gemm_tc(nullptr, 8, reltab, hd, gp, false, 0, e->num_sms, st, global ? 256 : 128, &tA));
   }
   ProfScope ps2(global ? PC_ATTN_GLOB : PC_ATTN_WIN, st);
@@ -810,7 +818,7 @@ static int gemm_enc(Engine* e, cudaStream_t st, const __half* A, int lda, const 
   p.out = out; p.ldc = ldc;
   p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.tiles_m = p.tiles_n = 0;
-  p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f; p.dbg = nullptr; p.accumulate = accumulate;
+  p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f; p.dbg = nullptr; p.dbg_mode = 0; p.accumulate = accumulate;
   ProfScope ps(PC_GEMM, st);
   return launch_gemm_tc(A, lda, W, K, p, out_half, act, e->num_sms, st, 0);
 }
@@ -872,7 +880,7 @@ static int gemm_dec(Engine* e, cudaStream_t st, const __half* A3, const __half* 
                     const float* bias, const float* res, int ldr, int res_mod, int accumulate = 0) {
   GemmParams p;
   p.M = M; p.N = N; p.K = K3; p.out = out; p.ldc = ldc; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
-  p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f; p.dbg = nullptr; p.accumulate = accumulate;
+  p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f; p.dbg = nullptr; p.dbg_mode = 0; p.accumulate = accumulate;
   return launch_gemm_tc(A3, K3, W3, K3, p, false, 0, e->num_sms, st, 0);
 }
 
@@ -1043,6 +1051,8 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
 using namespace samrs;
 static void* g_gemm_dbg = nullptr;      // device buffer of 4096 u64 for gemm pipeline traces (tests/tools only)
 extern "C" void samrs_test_set_gemm_trace(void* dev_buf) { g_gemm_dbg = dev_buf; }
+static int g_gemm_mode = 0;             // GemmParams::dbg_mode for the pipeline experiments in tools/gemm_trace.py
+extern "C" void samrs_test_set_gemm_mode(int mode) { g_gemm_mode = mode; }
 extern "C" void samrs_test_set_attn_trace(void* dev_buf) { samrs::g_attn_dbg = dev_buf; }
 
 struct LaunchScope {
@@ -1243,6 +1253,7 @@ int samrs_test_gemm(void* engine, const void* A, const void* B, int M, int N, in
   p.M = M; p.N = N; p.K = K; p.out = out; p.ldc = N; p.bias = bias; p.res = res; p.ldr = N; p.res_mod = 0; p.tiles_m = p.tiles_n = 0;
   p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f;
   p.dbg = static_cast<unsigned long long*>(g_gemm_dbg);
+  p.dbg_mode = g_gemm_mode;
   p.accumulate = 0;
   if (res != nullptr && res == out && !out_half) { p.res = nullptr; p.accumulate = 1; }   // in-place residual -> TMA reduce-add
   return set_err(e, launch_gemm_tc(static_cast<const __half*>(A), K, static_cast<const __half*>(B), K, p, out_half != 0, act_gelu, e->num_sms,

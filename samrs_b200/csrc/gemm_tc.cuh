@@ -31,6 +31,7 @@ struct GemmParams {
   float out_scale;      // accumulator is multiplied by this before bias/residual (split-weight scaling); 0 -> 1
   unsigned long long* dbg;   // optional: CTA 0 records clock64() at pipeline events (tools/gemm_trace.py)
   int accumulate;       // fp32 output only: out += result (TMA reduce-add) instead of out = result
+  int dbg_mode;         // tools only (results are garbage): bit0 skip TMA loads, bit1 skip MMAs, bit2 skip the epilogue
 };
 __device__ __forceinline__ void gemm_dbg(const GemmParams& p, int slot) {
   if (p.dbg != nullptr && blockIdx.x == 0 && slot < 4096) p.dbg[slot] = clock64();
@@ -118,7 +119,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
       for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
     }
     uint8_t* buf = stage;
-    if (lane == 0) tma_store_wait_read<0>();  // the previous chunk's store has finished reading the staging block
+    if (elect_one()) tma_store_wait_read<0>();  // the previous chunk's store has finished reading the staging block
     __syncwarp();
     if (OUT_HALF) {
 #pragma unroll
@@ -137,7 +138,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     }
     fence_proxy_async_smem();
     __syncwarp();
-    if (lane == 0) {
+    if (elect_one()) {                        // same lane every time (full-warp mask): bulk groups are per thread
       if (!OUT_HALF && p.accumulate) tma_reduce_add_3d(tmC, buf, n0 + c * 32, row0, bt);
       else tma_store_3d(tmC, buf, n0 + c * 32, row0, bt);
       tma_store_commit();
@@ -207,10 +208,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (CM == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 0) { gemm_dbg(p, 1); }
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop with warp-uniform state and one elected lane issues: under a divergent `lane == 0`
+    // branch the compiler cannot prove the operands uniform and wraps every TMA / MMA instruction in an
+    // ELECT + R2UR.BROADCAST + BRA.U.ANY waterfall loop, which cost ~500 clk per k-block (profiles/r01_gemm_trace.txt).
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int u = first; u < num_units; u += stride) {
@@ -222,43 +227,58 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + GEMM_BM * 128;
-          mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-          if (p.a_rank3) tma_load_3d(sa, &tmA, &full[stage], kb * GEMM_BK, bt, m0);
-          else tma_load_2d(sa, &tmA, &full[stage], kb * GEMM_BK, m0);
-          if (CM == 2) tma_load_2d_mcast(sb + crank * (BN / 2) * 128, &tmB, &full[stage], kb * GEMM_BK, n0 + crank * (BN / 2), 0x3);
-          else tma_load_2d(sb, &tmB, &full[stage], kb * GEMM_BK, n0);
+          if (p.dbg_mode & 1) {
+            if (elect_one()) mbar_arrive(&full[stage]);
+          } else if (elect_one()) {
+            mbar_expect_tx(&full[stage], Cfg::kStageBytes);
+            if (p.a_rank3) tma_load_3d(sa, &tmA, &full[stage], kb * GEMM_BK, bt, m0);
+            else tma_load_2d(sa, &tmA, &full[stage], kb * GEMM_BK, m0);
+            if (CM == 2) tma_load_2d_mcast(sb + crank * (BN / 2) * 128, &tmB, &full[stage], kb * GEMM_BK, n0 + crank * (BN / 2), 0x3);
+            else tma_load_2d(sb, &tmB, &full[stage], kb * GEMM_BK, n0);
+          }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ---------------------------------------------------------------- MMA issuer
-    if (lane == 0) {
+    // ---------------------------------------------------------------- MMA issuer (warp-uniform loop, elected lane issues)
+    {
       constexpr uint32_t idesc = umma_idesc_f16(GEMM_BM, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
       uint32_t aphase = 0;
-      for (int u = first; u < num_units; u += stride) {
+      int ti = 0;
+      for (int u = first; u < num_units; u += stride, ++ti) {
+        gemm_dbg(p, 16 + ti * 64 + 0);
         mbar_wait(&tempty[as], aphase ^ 1);
         tc_fence_after();
+        gemm_dbg(p, 16 + ti * 64 + 1);
         const uint32_t d_tmem = tmem_base + uint32_t(as * BN);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
+          if (kb < 40) gemm_dbg(p, 16 + ti * 64 + 2 + kb);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + GEMM_BM * 128;
           const uint64_t da = umma_desc_sw128(sa);
           const uint64_t db = umma_desc_sw128(sb);
+          if (elect_one()) {
+            if (!(p.dbg_mode & 2)) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advance 16 fp16 (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
-            tc_mma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+              for (int k = 0; k < GEMM_BK / 16; ++k) {
+                // advance 16 fp16 (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
+                tc_mma_f16(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+              }
+            }
+            if (CM == 2) tc_commit_mcast(&empty[stage], 0x3); else tc_commit(&empty[stage]);
+            if (kb == num_kb - 1) tc_commit(&tfull[as]);
           }
-          if (CM == 2) tc_commit_mcast(&empty[stage], 0x3); else tc_commit(&empty[stage]);
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        tc_commit(&tfull[as]);
+        gemm_dbg(p, 16 + ti * 64 + 60);
         as ^= 1;
         if (as == 0) aphase ^= 1;
       }
@@ -270,7 +290,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* my_stage = epi_stage + (warp - 4) * 4096;
     constexpr int NCH = BN / 32, SPLIT = (NCH + 1) / 2;
     const int cb = (warp < 8) ? 0 : SPLIT, ce = (warp < 8) ? SPLIT : NCH;
-    int as = 0;
+    int as = 0, eti = 0;
     uint32_t aphase = 0;
     for (int u = first; u < num_units; u += stride) {
       const int t = unit_to_tile(u);
@@ -281,20 +301,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       gemm_load_bias<BN>(p, n0, lane, bias_r);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
+      if (warp == 4 && lane == 0) gemm_dbg(p, 16 + eti * 64 + 61);
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, bt, oscale, my_stage, lane, bias_r, cb, ce);
+      if (!(p.dbg_mode & 4))
+        gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, bt, oscale, my_stage, lane, bias_r, cb, ce);
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[as]);
+      if (warp == 4 && lane == 0) gemm_dbg(p, 16 + eti * 64 + 62);
+      ++eti;
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-    if (lane == 0) tma_store_wait_all();
+    if (elect_one()) tma_store_wait_all();
   }
 
   tc_fence_before();
+  if (threadIdx.x == 0) gemm_dbg(p, 2);
   if (CM == 2) cluster_sync_all(); else __syncthreads();     // the peer may still multicast into / signal this CTA
+  if (threadIdx.x == 0) gemm_dbg(p, 3);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);

@@ -74,7 +74,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs)
-    if (lane == 0) {
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int t = pair; t < num_tiles; t += num_pairs) {
@@ -85,16 +85,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + GEMM_BM * 128;
           const uint32_t lead_full = mapa_u32(&full[stage], 0);
-          if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
-          tma_load_2d_pair(sa, &tmA, lead_full, kb * GEMM_BK, m0);
-          tma_load_2d_pair(sb, &tmB, lead_full, kb * GEMM_BK, n0);
+          if (elect_one()) {
+            if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
+            tma_load_2d_pair(sa, &tmA, lead_full, kb * GEMM_BK, m0);
+            tma_load_2d_pair(sb, &tmB, lead_full, kb * GEMM_BK, n0);
+          }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer (leader CTA only)
-    if (lane == 0 && rank == 0) {
+    if (rank == 0) {
       constexpr uint32_t idesc = umma_idesc_f16(256, BN, 0, 0);
       int stage = 0;
       uint32_t phase = 0;
@@ -114,13 +117,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t sb = sa + GEMM_BM * 128;
           const uint64_t da = umma_desc_sw128(sa);
           const uint64_t db = umma_desc_sw128(sb);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < GEMM_BK / 16; ++k)
-            tc_mma_f16_pair(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
-          tc_commit_pair(&empty[stage], 0x3);
+            for (int k = 0; k < GEMM_BK / 16; ++k)
+              tc_mma_f16_pair(d_tmem, da + uint64_t(2 * k), db + uint64_t(2 * k), idesc, (kb | k) != 0);
+            tc_commit_pair(&empty[stage], 0x3);
+            if (kb == num_kb - 1) tc_commit_pair(&tfull[as], 0x3);
+          }
+          __syncwarp();
           if (++stage == S) { stage = 0; phase ^= 1; }
         }
-        tc_commit_pair(&tfull[as], 0x3);
         gemm_dbg(p, 16 + ti * 64 + 60);
         ++ti;
         as ^= 1;
@@ -154,7 +160,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-    if (lane == 0) tma_store_wait_all();
+    if (elect_one()) tma_store_wait_all();
   }
 
   tc_fence_before();
