@@ -171,17 +171,18 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   bool pair = force_bn >= 1000 && force_bn < 2000;
   bool mcast = force_bn >= 2000;
   if (force_bn == 0 && p.M == 4096 && p.batch == 1 && (p.N == 1280 || p.N == 3840 || p.N == 5120) && num_sms == 148) {
-    // ViT-H shapes: measured best configurations (profiles/r01_gemm_sweep_v3.json)
-    bn = (p.N == 1280) ? 160 : (p.N == 3840 ? 224 : 256);
-    // experiment hook: SAMRS_BN="n1280,n3840,n5120" (e.g. "256,256,256") overrides the table
+    // ViT-H shapes: measured best configurations (profiles/r01_gemm_sweep_v4.json): the CTA-pair kernel everywhere
+    // (it halves the B bytes each SM pulls from L2; 1-CTA tiles are feed-bound once the issue loop is tight)
+    bn = (p.N == 1280) ? 160 : 224;
+    pair = true;
+    // experiment hook: SAMRS_BN="n1280,n3840,n5120" with force_bn codes (e.g. "160,224,256" = 1-CTA kernels)
     static int env_bn[3] = {-1, 0, 0};
     if (env_bn[0] < 0) {
       env_bn[0] = 0;
       if (const char* s = getenv("SAMRS_BN")) sscanf(s, "%d,%d,%d", &env_bn[0], &env_bn[1], &env_bn[2]);
     }
     const int ov = env_bn[p.N == 1280 ? 0 : (p.N == 3840 ? 1 : 2)];
-    if (ov > 0) bn = ov;
-    pair = false;
+    if (ov > 0) { bn = ov % 1000; pair = ov >= 1000 && ov < 2000; }
     static const bool use_mcast = getenv("SAMRS_GEMM_MCAST") != nullptr;
     mcast = use_mcast;
   } else if (force_bn == 0) {

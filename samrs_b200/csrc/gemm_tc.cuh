@@ -36,12 +36,21 @@ struct GemmParams {
 __device__ __forceinline__ void gemm_dbg(const GemmParams& p, int slot) {
   if (p.dbg != nullptr && blockIdx.x == 0 && slot < 4096) p.dbg[slot] = clock64();
 }
+// wall-clock span of the whole grid (slots 10 / 11 = min start / max end over CTAs, ns) and of CTA 0 (12 / 13)
+__device__ __forceinline__ void gemm_dbg_wall(const GemmParams& p, bool end) {
+  if (p.dbg == nullptr) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  if (end) atomicMax(p.dbg + 11, t); else atomicMin(p.dbg + 10, t);
+  if (blockIdx.x == 0) p.dbg[end ? 13 : 12] = t;
+}
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // one 128-byte swizzle atom of fp16
 constexpr int GEMM_EPI_WARPS = 8;                    // warps 4..11: two column groups of four (TMEM lane quadrant = warp % 4)
 constexpr int GEMM_THREADS = 128 + 32 * GEMM_EPI_WARPS;
-constexpr int GEMM_EPI_SMEM = GEMM_EPI_WARPS * 4096;       // one 32x32 fp32 staging block per epilogue warp
+constexpr int GEMM_EPI_WARP_SMEM = 8192;                  // per epilogue warp: two 32x32 fp32 or four 32x32 fp16 staging blocks
+constexpr int GEMM_EPI_SMEM = GEMM_EPI_WARPS * GEMM_EPI_WARP_SMEM;
 
 template <int BN>
 struct GemmCfg {
@@ -52,23 +61,72 @@ struct GemmCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/ + GEMM_EPI_SMEM;
 };
 
-// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, i.e. far below the
-// fp16 rounding of the result): one MUFU rcp, one MUFU ex2 and six FMAs instead of erff's ~30 instructions, which made the
-// lin1 epilogue longer than its main loop.
+// GELU(x) = x/2 (1 + erf(x / sqrt 2)) = (h + |h|) - |h| erfc(z) with h = x/2, z = |x| / sqrt 2, and
+// erfc(z) ~= 2^(-z Q(z)) on [0, 4] (Q = degree-5 least-squares fit of -log2(erfc z) / z, tools/fit_gelu.py): |error| < 3e-7,
+// far below the fp16 rounding of the result.  One MUFU op and ten FP32 ops per element: the epilogue of lin1 is bound
+// by MUFU / issue slots, erff costs ~30 instructions and the Abramowitz-Stegun 7.1.26 form used before two MUFU ops.
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  float t, ex;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));      // MUFU, ~1 ulp
-  float poly = fmaf(t, 1.061405429f, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  poly *= t;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(ex) : "f"(-z * z * 1.4426950408889634f));  // MUFU, ~2 ulp
-  const float e = 1.0f - poly * ex;                                        // erf(|x|/sqrt2)
-  return 0.5f * x + 0.5f * fabsf(x) * e;                                   // x * (1 + sign(x) erf) / 2
+  const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float q = fmaf(z, -2.635702863e-04f, 4.330650429e-03f);
+  q = fmaf(q, z, -3.223223820e-02f);
+  q = fmaf(q, z, 1.509066050e-01f);
+  q = fmaf(q, z, 9.176831254e-01f);
+  q = fmaf(q, z, 1.627991484e+00f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-z * q));               // MUFU, ~2 ulp
+  const float h = 0.5f * x;
+  return fmaf(-fabsf(h), e, h + fabsf(h));
 }
 
+// fp16-output epilogue (qkv, lin1): 32-column chunks are processed in pairs - both tcgen05.ld are in flight together, the
+// two converted 32x32 fp16 blocks are staged side by side and handed to the TMA unit behind ONE proxy fence / elect -
+// and the four 2 KiB staging blocks of the warp rotate, so the warp only waits for the store issued two pairs ago.
+template <int BN, int ACT>
+__device__ __forceinline__ void gemm_epilogue_warp_half(const GemmParams& p, const CUtensorMap* tmC, uint32_t t_addr, int row0, int n0,
+                                                        int bt, float oscale, uint8_t* stage, uint32_t& nstaged, int lane,
+                                                        const float (&bias_r)[BN / 32], int chunk_begin, int chunk_end) {
+  constexpr int NCH = BN / 32;
+  auto convert = [&](const uint32_t (&v)[32], float bias_c, uint8_t* buf) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        f[i] = fmaf(__uint_as_float(v[8 * j + i]), oscale, __shfl_sync(0xffffffffu, bias_c, 8 * j + i));
+        if (ACT == 1) f[i] = gelu_erf(f[i]);
+      }
+      __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+      __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(buf + lane * 64 + j * 16) = pk;
+    }
+  };
+#pragma unroll
+  for (int c = 0; c < NCH; c += 2) {
+    if (c < chunk_begin || c >= chunk_end) continue;
+    if (n0 + c * 32 >= p.N) break;
+    const bool two = (c + 1 < NCH) && (c + 1 < chunk_end) && (n0 + (c + 1) * 32 < p.N);     // warp-uniform
+    uint32_t v0[32], v1[32];
+    tmem_ld32(t_addr + uint32_t(c * 32), v0);
+    if (two) tmem_ld32(t_addr + uint32_t((c + 1 < NCH ? c + 1 : c) * 32), v1);
+    uint8_t* buf = stage + (nstaged & 1) * (GEMM_EPI_WARP_SMEM / 2);
+    ++nstaged;
+    if (elect_one()) tma_store_wait_read<1>();   // the pair staged two steps ago has been read by the TMA unit
+    __syncwarp();
+    tc_wait_ld();
+    convert(v0, bias_r[c], buf);
+    if (two) convert(v1, bias_r[c + 1 < NCH ? c + 1 : c], buf + 2048);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one()) {                           // same lane every time (full-warp mask): bulk groups are per thread
+      tma_store_3d(tmC, buf, n0 + c * 32, row0, bt);
+      if (two) tma_store_3d(tmC, buf + 2048, n0 + (c + 1) * 32, row0, bt);
+      tma_store_commit();
+    }
+  }
+}
 
 // Epilogue of one accumulator tile, executed by one warp for its 32 TMEM lanes (rows row0 .. row0+31), 32 columns at
 // a time: tcgen05.ld -> scale + bias (+ residual) + activation in registers -> the warp's 32x32 block is staged in
@@ -80,8 +138,12 @@ __device__ __forceinline__ float gelu_erf(float x) {
 // ahead), and the stores never stall the warp.
 template <int BN, bool OUT_HALF, int ACT>
 __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CUtensorMap* tmC, uint32_t t_addr, int row0, int n0,
-                                                   int bt, float oscale, uint8_t* stage /*4 KiB, 1024-B aligned*/, int lane,
-                                                   const float (&bias_r)[BN / 32], int chunk_begin, int chunk_end) {
+                                                   int bt, float oscale, uint8_t* stage /*8 KiB, 1024-B aligned*/, uint32_t& nstaged,
+                                                   int lane, const float (&bias_r)[BN / 32], int chunk_begin, int chunk_end) {
+  if constexpr (OUT_HALF) {
+    gemm_epilogue_warp_half<BN, ACT>(p, tmC, t_addr, row0, n0, bt, oscale, stage, nstaged, lane, bias_r, chunk_begin, chunk_end);
+    return;
+  }
   constexpr int NCH = BN / 32;
   const int row = row0 + lane;
   const float* res_row = nullptr;
@@ -118,8 +180,12 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
 #pragma unroll
       for (int j = 0; j < 32; ++j) f[j] = gelu_erf(f[j]);
     }
-    uint8_t* buf = stage;
-    if (elect_one()) tma_store_wait_read<0>();  // the previous chunk's store has finished reading the staging block
+    // staging blocks rotate (2 x 4 KiB fp32 / 4 x 2 KiB fp16): the block about to be overwritten was handed to the TMA
+    // unit NBUF chunks ago, so the warp only waits for that store to have read it while the newer ones are in flight
+    constexpr int NBUF = OUT_HALF ? 4 : 2;
+    uint8_t* buf = stage + (nstaged % NBUF) * (GEMM_EPI_WARP_SMEM / NBUF);
+    ++nstaged;
+    if (elect_one()) tma_store_wait_read<NBUF - 1>();
     __syncwarp();
     if (OUT_HALF) {
 #pragma unroll
@@ -187,6 +253,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int num_units = (CM == 2) ? num_tiles / 2 : num_tiles;
   auto unit_to_tile = [&](int u) { return (CM == 2) ? ((u % (p.tiles_m / 2)) * 2 + crank + (u / (p.tiles_m / 2)) * p.tiles_m) : u; };
 
+  if (threadIdx.x == 0) gemm_dbg_wall(p, false);
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
@@ -287,8 +354,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ---------------------------------------------------------------- epilogue
     const int q = warp & 3;                       // TMEM lane quadrant of this warp
     const float oscale = (p.out_scale != 0.f) ? p.out_scale : 1.0f;
-    uint8_t* my_stage = epi_stage + (warp - 4) * 4096;
-    constexpr int NCH = BN / 32, SPLIT = (NCH + 1) / 2;
+    uint8_t* my_stage = epi_stage + (warp - 4) * GEMM_EPI_WARP_SMEM;
+    uint32_t nstaged = 0;
+    constexpr int NCH = BN / 32, SPLIT = OUT_HALF ? ((NCH + 1) / 4) * 2 : (NCH + 1) / 2;   // fp16: whole chunk pairs per group
     const int cb = (warp < 8) ? 0 : SPLIT, ce = (warp < 8) ? SPLIT : NCH;
     int as = 0, eti = 0;
     uint32_t aphase = 0;
@@ -304,7 +372,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (warp == 4 && lane == 0) gemm_dbg(p, 16 + eti * 64 + 61);
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
       if (!(p.dbg_mode & 4))
-        gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, bt, oscale, my_stage, lane, bias_r, cb, ce);
+        gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, bt, oscale, my_stage, nstaged, lane, bias_r, cb, ce);
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();
@@ -320,7 +388,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   tc_fence_before();
   if (threadIdx.x == 0) gemm_dbg(p, 2);
   if (CM == 2) cluster_sync_all(); else __syncthreads();     // the peer may still multicast into / signal this CTA
-  if (threadIdx.x == 0) gemm_dbg(p, 3);
+  if (threadIdx.x == 0) { gemm_dbg(p, 3); gemm_dbg_wall(p, true); }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);

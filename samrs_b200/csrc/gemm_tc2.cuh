@@ -32,7 +32,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   using Cfg = Gemm2Cfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
-  if (threadIdx.x == 0) gemm_dbg(p, 0);
+  if (threadIdx.x == 0) { gemm_dbg(p, 0); gemm_dbg_wall(p, false); }
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* epi_stage = smem + S * Cfg::kStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(epi_stage + GEMM_EPI_SMEM);
@@ -137,8 +137,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     // ---------------------------------------------------------------- epilogue (both CTAs, own 128 rows)
     const int q = warp & 3;
     const float oscale = (p.out_scale != 0.f) ? p.out_scale : 1.0f;
-    uint8_t* my_stage = epi_stage + (warp - 4) * 4096;
-    constexpr int NCH = BN / 32, SPLIT = (NCH + 1) / 2;
+    uint8_t* my_stage = epi_stage + (warp - 4) * GEMM_EPI_WARP_SMEM;
+    uint32_t nstaged = 0;
+    constexpr int NCH = BN / 32, SPLIT = OUT_HALF ? ((NCH + 1) / 4) * 2 : (NCH + 1) / 2;   // fp16: whole chunk pairs per group
     const int cb = (warp < 8) ? 0 : SPLIT, ce = (warp < 8) ? SPLIT : NCH;
     int as = 0, eti = 0;
     uint32_t aphase = 0;
@@ -151,7 +152,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       tc_fence_after();
       if (warp == 4 && lane == 0) gemm_dbg(p, 16 + eti * 64 + 61);
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, 0, oscale, my_stage, lane, bias_r, cb, ce);
+      gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, 0, oscale, my_stage, nstaged, lane, bias_r, cb, ce);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[as], 0));
@@ -166,7 +167,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_before();
   if (threadIdx.x == 0) gemm_dbg(p, 2);
   cluster_sync_all();                               // nobody exits (or frees TMEM) while the pair still signals
-  if (threadIdx.x == 0) gemm_dbg(p, 3);
+  if (threadIdx.x == 0) { gemm_dbg(p, 3); gemm_dbg_wall(p, true); }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
