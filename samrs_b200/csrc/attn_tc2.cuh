@@ -334,16 +334,19 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           rk_next[i] = *reinterpret_cast<uint32_t*>(&h);
         }
       } else {
-        float rv[32];
+        // windowed: the GEMM epilogue already produced fp16(G / scale_log2e); gather this row's 14 + 14 entries
+        const __half* rrow = p.rel16 + (size_t(head) * 4096 + (valid ? ty * 64 + tx : 0)) * NP;
+        const __half zero = __float2half_rn(0.f);
+        __half rv[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) rv[i] = 0.f;
+        for (int i = 0; i < 32; ++i) rv[i] = zero;
 #pragma unroll
-        for (int i = 0; i < KBY; ++i) rv[i] = valid ? __ldg(relrow + qh + (SS - 1) - i) * inv_scale : 0.f;
+        for (int i = 0; i < KBY; ++i) rv[i] = valid ? __ldg(rrow + qh + (SS - 1) - i) : zero;
 #pragma unroll
-        for (int i = 0; i < BX; ++i) rv[KBY + i] = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - i) * inv_scale : 0.f;
+        for (int i = 0; i < BX; ++i) rv[KBY + i] = valid ? __ldg(rrow + (2 * SS - 1) + qw + (SS - 1) - i) : zero;
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          __half2 h = __floats2half2_rn(rv[2 * i], rv[2 * i + 1]);
+          __half2 h = __halves2half2(rv[2 * i], rv[2 * i + 1]);
           rk_next[i] = *reinterpret_cast<uint32_t*>(&h);
         }
       }

@@ -403,6 +403,18 @@ static int ln_rows(cudaStream_t st, const float* in, int ld_in, const float* g, 
   const int threads = 256, rows_per_block = threads / 32;
   const int grid = (rows + rows_per_block - 1) / rows_per_block;
   if (C % 4 != 0) SAMRS_FAIL("layernorm: C must be a multiple of 4");
+  if constexpr (sizeof(OutT) == 2 && ACT == 0) {
+    static const bool no_stream = getenv("SAMRS_LN_ROWS") != nullptr;   // experiment hook: the one-row-per-warp kernel
+    if (!no_stream && rows >= 1024 && (C == 1280 || C == 1024 || C == 768)) {
+      const int g4 = (rows + 3) / 4;
+      if (C == 1280) ln_rows_stream_kernel<10><<<g4, 64, 0, st>>>(in, ld_in, g, b, eps, reinterpret_cast<__half*>(out), ld_out, rows);
+      else if (C == 1024) ln_rows_stream_kernel<8><<<g4, 64, 0, st>>>(in, ld_in, g, b, eps, reinterpret_cast<__half*>(out), ld_out, rows);
+      else ln_rows_stream_kernel<6><<<g4, 64, 0, st>>>(in, ld_in, g, b, eps, reinterpret_cast<__half*>(out), ld_out, rows);
+      SAMRS_CUDA_OK(cudaGetLastError());
+      count_launch();
+      return 0;
+    }
+  }
   if (nv <= 32) ln_rows_kernel<OutT, ACT, 1><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
   else if (nv <= 64) ln_rows_kernel<OutT, ACT, 2><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
   else if (nv <= 192) ln_rows_kernel<OutT, ACT, 6><<<grid, threads, 0, st>>>(in, ld_in, g, b, eps, out, ld_out, rows, C);
@@ -459,11 +471,17 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
     GemmParams gp;
     gp.M = 4096; gp.N = NP; gp.K = hd; gp.out = e->rel; gp.ldc = NP; gp.bias = nullptr; gp.res = nullptr; gp.ldr = 0; gp.res_mod = 0;
     gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f; gp.dbg = nullptr; gp.dbg_mode = 0; gp.accumulate = 0;
-    SAMRS_TRY(launch_gemm_tc(nullptr, 8, reltab, hd, gp, false, 0, e->num_sms, st, global ? 256 : 128, &tA));
+    // windowed blocks (attention v2): the epilogue writes fp16(G / scale_log2e), the value the attention kernel feeds to its
+    // bias MMA, which halves the bytes written here and gathered there; global blocks keep the fp32 table (scalar rel_h terms)
+    static const bool v1 = getenv("SAMRS_ATTN_V1") != nullptr;
+    const bool g16 = !global && !v1;
+    if (g16) gp.out_scale = 1.0f / ((1.0f / sqrtf(float(hd))) * 1.4426950408889634f);
+    SAMRS_TRY(launch_gemm_tc(nullptr, 8, reltab, hd, gp, g16, 0, e->num_sms, st, global ? 256 : 128, &tA));
   }
   ProfScope ps2(global ? PC_ATTN_GLOB : PC_ATTN_WIN, st);
   AttnParams p;
   p.rel = e->rel;
+  p.rel16 = reinterpret_cast<const __half*>(e->rel);
   p.out = out;
   p.D = D;
   p.heads = e->heads;

@@ -39,6 +39,64 @@ __global__ void preprocess_im2col_kernel(const uint8_t* __restrict__ img, int H,
 }
 
 // ------------------------------------------------------------------------------------------------
+// Encoder LayerNorm, streaming form: a block of 2 warps owns 4 consecutive rows (1024 blocks for 4096 rows = 7 blocks on
+// almost every one of the 148 SMs instead of 3-or-4 blocks of 8 rows), each warp normalises 2 rows and loads the second
+// while it reduces / stores the first, so the read and write bursts overlap instead of following each other.
+// Same arithmetic (two-pass mean / biased variance, same summation order) as ln_rows_kernel below.
+// ------------------------------------------------------------------------------------------------
+template <int MAXV /* float4 per lane, exact: C == 128 * MAXV */>
+__global__ void __launch_bounds__(64) ln_rows_stream_kernel(const float* __restrict__ in, int ld_in, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float eps, __half* __restrict__ out,
+                                                            int ld_out, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int row0 = blockIdx.x * 4 + (threadIdx.x >> 5) * 2;
+  if (row0 >= rows) return;
+  constexpr float Cf = float(128 * MAXV);
+  float4 v[2][MAXV];
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    const float4* src = reinterpret_cast<const float4*>(in + size_t(row0 + rr < rows ? row0 + rr : row0) * ld_in);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) v[rr][i] = src[lane + 32 * i];
+  }
+#pragma unroll
+  for (int rr = 0; rr < 2; ++rr) {
+    if (row0 + rr >= rows) break;
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) s += (v[rr][i].x + v[rr][i].y) + (v[rr][i].z + v[rr][i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / Cf;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const float a = v[rr][i].x - mean, b = v[rr][i].y - mean, c = v[rr][i].z - mean, d = v[rr][i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / Cf + eps);
+    uint2* dst = reinterpret_cast<uint2*>(out + size_t(row0 + rr) * ld_out);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int k = lane + 32 * i;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + k);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + k);
+      const float y0 = (v[rr][i].x - mean) * rstd * g.x + b.x;
+      const float y1 = (v[rr][i].y - mean) * rstd * g.y + b.y;
+      const float y2 = (v[rr][i].z - mean) * rstd * g.z + b.z;
+      const float y3 = (v[rr][i].w - mean) * rstd * g.w + b.w;
+      __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      dst[k] = pk;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Row LayerNorm (nn.LayerNorm / LayerNorm2d over a contiguous channel row): one warp per row,
 // two-pass mean / biased variance in registers.  OutT = __half feeds the next tensor-core GEMM,
 // OutT = float is used by the decoder.  ACT 1 = GELU(erf) (output_upscaling, mask_downscaling).
