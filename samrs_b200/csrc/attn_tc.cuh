@@ -26,7 +26,7 @@ namespace samrs {
 struct AttnParams {
   const float* rel;     // [heads][4096][NP] fp32 (NP = 256 global / 64 windowed), log2(e) * q.[rel_pos_h ; rel_pos_w]:
                         //   rel_h[kh] = rel[qh - kh + S-1],  rel_w[kw] = rel[(2S-1) + qw - kw + S-1]
-  const __half* rel16;  // attention v2, windowed blocks: the same table already divided by scale_log2e and rounded to fp16
+  const __half* rel16;  // attention v2: the same table already divided by scale_log2e and rounded to fp16
                         //   (written by the rel-pos GEMM's epilogue; it is exactly the value the kernel used to compute)
   __half* out;          // [4096][D] fp16, head-major columns (h*HD + c)
   int D;                // embed dim

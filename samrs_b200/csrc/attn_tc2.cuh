@@ -322,15 +322,16 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int qy = w ? qy1 : qy0;
       const int ty = qy + r / BX, tx = x0 + r % BX;
       const bool valid = (r < QR) && ty < 64 && tx < 64;
-      const float* relrow = p.rel + (size_t(head) * 4096 + (valid ? ty * 64 + tx : 0)) * NP;
       const int qh = qy - ky0 + r / BX, qw = r % BX;
-      const float inv_scale = 1.0f / p.scale_log2e;
       if (NKT > 1) {
+        // the rel-pos GEMM's epilogue wrote fp16(G / scale_log2e), i.e. the entries of the bias operand R themselves
+        const __half* rrow = p.rel16 + (size_t(head) * 4096 + (valid ? ty * 64 + tx : 0)) * NP;
+        const __half zero = __float2half_rn(0.f);
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          const float a0 = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - 2 * i) * inv_scale : 0.f;
-          const float a1 = valid ? __ldg(relrow + (2 * SS - 1) + qw + (SS - 1) - (2 * i + 1)) * inv_scale : 0.f;
-          __half2 h = __floats2half2_rn(a0, a1);
+          const __half a0 = valid ? __ldg(rrow + (2 * SS - 1) + qw + (SS - 1) - 2 * i) : zero;
+          const __half a1 = valid ? __ldg(rrow + (2 * SS - 1) + qw + (SS - 1) - (2 * i + 1)) : zero;
+          __half2 h = __halves2half2(a0, a1);
           rk_next[i] = *reinterpret_cast<uint32_t*>(&h);
         }
       } else {
@@ -360,8 +361,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int ty = qy + r / BX, tx = x0 + r % BX;
       const bool valid = (r < QR) && ty < 64 && tx < 64;
       const int token = ty * 64 + tx;
-      const float* relrow = p.rel + (size_t(head) * 4096 + (valid ? token : 0)) * NP;
-      const int qh = qy - ky0 + r / BX, qw = r % BX;
+      const __half* relrow = p.rel16 + (size_t(head) * 4096 + (valid ? token : 0)) * NP;
+      const int qh = qy - ky0 + r / BX;
       // this row's packed rel-pos operand R was prefetched during the previous unit (rk_next): store it to tensor memory
       if constexpr (C::RK == 64) tmem_st32(wg_addr + C::R_OFF, rk_next); else tmem_st16(wg_addr + C::R_OFF, rk_next);
       tc_wait_st();
@@ -374,7 +375,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         constexpr int NG = (NKT > 1) ? KBY : 1;
         float relh[NG];
 #pragma unroll
-        for (int i = 0; i < NG; ++i) relh[i] = (NKT > 1 && valid) ? __ldg(relrow + qh + (SS - 1) - (j * KBY + i)) : 0.f;
+        for (int i = 0; i < NG; ++i) relh[i] = (NKT > 1 && valid) ? __half2float(__ldg(relrow + qh + (SS - 1) - (j * KBY + i))) * p.scale_log2e : 0.f;
         if (tr && j == 0) attn_dbg(p, 64 * ui + 21 + 10 * w);
         mbar_wait(&s_full[w], sph);
         sph ^= 1;

@@ -471,10 +471,10 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
     GemmParams gp;
     gp.M = 4096; gp.N = NP; gp.K = hd; gp.out = e->rel; gp.ldc = NP; gp.bias = nullptr; gp.res = nullptr; gp.ldr = 0; gp.res_mod = 0;
     gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f; gp.dbg = nullptr; gp.dbg_mode = 0; gp.accumulate = 0;
-    // windowed blocks (attention v2): the epilogue writes fp16(G / scale_log2e), the value the attention kernel feeds to its
-    // bias MMA, which halves the bytes written here and gathered there; global blocks keep the fp32 table (scalar rel_h terms)
+    // attention v2: the epilogue writes fp16(G / scale_log2e), the value the attention kernel feeds to its bias MMA, which
+    // halves the bytes written here and gathered there (global blocks: 67 -> 34 MB per layer)
     static const bool v1 = getenv("SAMRS_ATTN_V1") != nullptr;
-    const bool g16 = !global && !v1;
+    const bool g16 = !v1;
     if (g16) gp.out_scale = 1.0f / ((1.0f / sqrtf(float(hd))) * 1.4426950408889634f);
     SAMRS_TRY(launch_gemm_tc(nullptr, 8, reltab, hd, gp, g16, 0, e->num_sms, st, global ? 256 : 128, &tA));
   }

@@ -160,6 +160,9 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   for (int c = 0; c < NCH; ++c) {
     if (c < chunk_begin || c >= chunk_end) continue;
     if (n0 + c * 32 >= p.N) break;
+    const bool trc = (p.dbg != nullptr) && (threadIdx.x >> 5) == 4 && lane == 0 && nstaged < 32;
+    const int tslot = 2048 + int(nstaged) * 8;
+    if (trc) gemm_dbg(p, tslot + 0);
     uint32_t v[32];
     tmem_ld32(t_addr + uint32_t(c * 32), v);
     float4 rc[8];
@@ -169,6 +172,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
       if (c + 1 < chunk_end) load_res(c + 1);
     }
     tc_wait_ld();
+    if (trc) gemm_dbg(p, tslot + 1);
     float f[32];
 #pragma unroll
     for (int j = 0; j < 32; ++j) f[j] = fmaf(__uint_as_float(v[j]), oscale, __shfl_sync(0xffffffffu, bias_r[c], j));
@@ -185,8 +189,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     constexpr int NBUF = OUT_HALF ? 4 : 2;
     uint8_t* buf = stage + (nstaged % NBUF) * (GEMM_EPI_WARP_SMEM / NBUF);
     ++nstaged;
+    if (trc) gemm_dbg(p, tslot + 2);
     if (elect_one()) tma_store_wait_read<NBUF - 1>();
     __syncwarp();
+    if (trc) gemm_dbg(p, tslot + 3);
     if (OUT_HALF) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -202,13 +208,16 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
       for (int j = 0; j < 8; ++j)
         *reinterpret_cast<float4*>(buf + lane * 128 + ((j ^ (lane & 7)) << 4)) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
     }
+    if (trc) gemm_dbg(p, tslot + 4);
     fence_proxy_async_smem();
     __syncwarp();
+    if (trc) gemm_dbg(p, tslot + 5);
     if (elect_one()) {                        // same lane every time (full-warp mask): bulk groups are per thread
       if (!OUT_HALF && p.accumulate) tma_reduce_add_3d(tmC, buf, n0 + c * 32, row0, bt);
       else tma_store_3d(tmC, buf, n0 + c * 32, row0, bt);
       tma_store_commit();
     }
+    if (trc) gemm_dbg(p, tslot + 6);
   }
 }
 

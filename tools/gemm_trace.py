@@ -22,12 +22,12 @@ for name, (M, N, K, half, useres) in shapes.items():
         line = f"{name:5s} cfg {cfg}:"
         for mode in ((0, 1, 2, 4, 5, 6, 3) if cfg < 1000 else (0,)):
             lib.samrs_test_set_gemm_mode(mode)
-            for _ in range(3): eng.test_gemm(A, B, out_half=half, bias=bias, res=r, gelu=gelu, force_bn=cfg)
+            for _ in range(3): eng.test_gemm(A, B, out_half=half, bias=bias, res=r, out=r, gelu=gelu, force_bn=cfg)
             ts = []
             for _ in range(10):
                 flush.zero_()
                 e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-                e0.record(); eng.test_gemm(A, B, out_half=half, bias=bias, res=r, gelu=gelu, force_bn=cfg); e1.record()
+                e0.record(); eng.test_gemm(A, B, out_half=half, bias=bias, res=r, out=r, gelu=gelu, force_bn=cfg); e1.record()
                 torch.cuda.synchronize(); ts.append(e0.elapsed_time(e1) * 1e3)
             line += f"  m{mode} {sorted(ts)[len(ts)//2]:6.1f}us"
         lib.samrs_test_set_gemm_mode(0)
@@ -35,9 +35,9 @@ for name, (M, N, K, half, useres) in shapes.items():
         if True:
             torch.cuda.synchronize(); buf.zero_(); buf[10] = 1 << 62
             if os.environ.get("TRACE_HOT"):          # trace the launch that follows 40 back-to-back ones (sustained clocks)
-                for _ in range(40): eng.test_gemm(A, B, out_half=half, bias=bias, res=r, gelu=gelu, force_bn=cfg)
+                for _ in range(40): eng.test_gemm(A, B, out_half=half, bias=bias, res=r, out=r, gelu=gelu, force_bn=cfg)
             lib.samrs_test_set_gemm_trace(buf.data_ptr())
-            eng.test_gemm(A, B, out_half=half, bias=bias, res=r, gelu=gelu, force_bn=cfg)
+            eng.test_gemm(A, B, out_half=half, bias=bias, res=r, out=r, gelu=gelu, force_bn=cfg)
             torch.cuda.synchronize()
             lib.samrs_test_set_gemm_trace(None)
             t = buf.cpu().tolist(); t0 = t[1] - 1400 if t[0] == 0 else t[0]
@@ -50,3 +50,8 @@ for name, (M, N, K, half, useres) in shapes.items():
                 d = [kbs[i + 1] - kbs[i] for i in range(len(kbs) - 1)]
                 print(f"   tile {ti}: mma_start {t[base]-t0} first_full {kbs[0] if kbs else None} kb min {min(d) if d else 0} med {sorted(d)[len(d)//2] if d else 0} "
                       f"max {max(d) if d else 0} issue_done {t[base+60]-t0} | epi {t[base+61]-t0 if t[base+61] else None} -> {t[base+62]-t0 if t[base+62] else None}")
+            if not half:
+                for ci in range(6):
+                    e = t[2048 + ci * 8: 2048 + ci * 8 + 7]
+                    if e[0] == 0: break
+                    print(f"   epi chunk {ci}: start {e[0]-t0}  ld {e[1]-e[0]}  math {e[2]-e[1]}  wait_read {e[3]-e[2]}  sts {e[4]-e[3]}  fence {e[5]-e[4]}  tma_issue {e[6]-e[5]}")
