@@ -60,6 +60,19 @@ int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int i
 int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_ids, int B,
                           uint8_t* label_map_inout, int H, int W, void* stream);
 
+/* instance payload on the device: uncompressed COCO run-length encoding and area of B masks.
+ * Replaces, per mask, the D2H of the bool mask + `maskUtils.encode(np.asfortranarray(mask))` + `np.sum(mask)`
+ * -- Generate Dataset/main_sam_hbox_semantic.py:200-203; run semantics as pinned in-repo by
+ * segment_anything/utils/amg.py:107-135 (mask_to_rle_pytorch): column-major pixel order, alternating run lengths
+ * starting with a run of zeros (a mask whose first pixel is set gets a leading 0), lengths sum to H*W.
+ * Exactly one source is non-NULL: `masks` (B,H,W) uint8 0/non-0 (torch.bool storage, e.g. predict_torch's masks), or
+ * `lowres` (B,256,256) logits of a 1024x1024 tile (H = W = 1024), thresholded after the same bilinear x4 upsample as
+ * samrs_postprocess without materialising the masks.
+ * counts_out[offsets_out[b] .. offsets_out[b+1]) are mask b's runs; offsets_out has B+1 entries, area_out B.
+ * Runs beyond `capacity` entries are not written: the caller checks offsets_out[B] <= capacity and retries. */
+int samrs_rle_encode(void* engine, const uint8_t* masks, const float* lowres, int B, int H, int W,
+                     uint32_t* counts_out, long long capacity, long long* offsets_out, long long* area_out, void* stream);
+
 /* device-side timing by kernel category (bench.py's roofline): enable=1 starts recording CUDA events around the
  * engine's launches on their stream; enable=0 synchronises and returns milliseconds / scope counts per category:
  * 0 tcgen05 GEMM, 1 windowed attention, 2 global attention, 3 rel-pos terms, 4 LayerNorm, 5 whole encode,

@@ -14,6 +14,7 @@
 #include "gemm_tc.cuh"
 #include "gemm_tc2.cuh"
 #include "simt.cuh"
+#include "rle.cuh"
 
 namespace samrs {
 
@@ -339,6 +340,10 @@ struct Engine {
   // per-image decoder cache
   float *src0, *K0, *V0, *Qi0;
   float* pp_full = nullptr;            // postprocess scratch for non-1024 sizes
+  uint32_t* rle_packed = nullptr;      // run-length encoder scratch: column-major bit planes [B][ceil(H/32)][W]
+  size_t rle_packed_words = 0;
+  long long* rle_runs = nullptr;       // [rle_runs_cap] runs per mask
+  int rle_runs_cap = 0;
   float* splitk_ws = nullptr;          // split-K partial sums of the token-side SGEMMs
   size_t splitk_ws_floats = 0;
   float* d_t2i_part = nullptr;         // [cap][8][16][8][18] key-chunk partials of the token->image attention
@@ -1201,6 +1206,47 @@ int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int i
     count_launch(2);
   }
   if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "postprocess launch failed"));
+  return 0;
+}
+
+int samrs_rle_encode(void* engine, const uint8_t* masks, const float* lowres, int B, int H, int W, uint32_t* counts_out,
+                     long long capacity, long long* offsets_out, long long* area_out, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B < 0 || H < 1 || W < 1) return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_encode: bad shape"));
+  if ((masks == nullptr) == (lowres == nullptr))
+    return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_encode: pass either bool masks or low-res logits"));
+  if (lowres != nullptr && (H != 1024 || W != 1024))
+    return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_encode: the fused low-res path needs a 1024x1024 tile (pass masks otherwise)"));
+  if (!offsets_out || !area_out || (!counts_out && capacity > 0))
+    return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_encode: null output"));
+  if (size_t(H) * size_t(W) >= (size_t(1) << 31)) return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_encode: mask too large"));
+  ProfScope ps(PC_EPILOGUE, st);
+  const int HW32 = (H + 31) / 32;
+  const size_t words = size_t(B > 0 ? B : 1) * HW32 * W;
+  if (words > e->rle_packed_words) {
+    if (e->alloc(&e->rle_packed, words) != 0) return set_err(e, 1);
+    e->rle_packed_words = words;
+  }
+  if (B + 1 > e->rle_runs_cap) {
+    if (e->alloc(&e->rle_runs, size_t(B) + 1) != 0) return set_err(e, 1);
+    e->rle_runs_cap = B + 1;
+  }
+  if (B > 0) {
+    for (int b0 = 0; b0 < B; b0 += 32768) {
+      const int nb = B - b0 < 32768 ? B - b0 : 32768;
+      if (masks) rle_pack_kernel<<<dim3((W + 127) / 128, HW32, nb), 128, 0, st>>>(masks + size_t(b0) * H * W, H, W, HW32, e->rle_packed + size_t(b0) * HW32 * W);
+      else rle_pack_lowres_kernel<<<dim3(8, 32, nb), 128, 0, st>>>(lowres + size_t(b0) * 65536, e->rle_packed + size_t(b0) * HW32 * W);
+    }
+    rle_scan_kernel<false><<<B, RLE_THREADS, 0, st>>>(e->rle_packed, H, W, HW32, e->rle_runs, area_out, nullptr, nullptr, 0);
+  }
+  rle_offsets_kernel<<<1, 32, 0, st>>>(e->rle_runs, B, offsets_out);
+  if (B > 0) rle_scan_kernel<true><<<B, RLE_THREADS, 0, st>>>(e->rle_packed, H, W, HW32, nullptr, nullptr, offsets_out, counts_out, capacity);
+  count_launch(B > 0 ? 4 : 1);
+  if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_encode launch failed"));
   return 0;
 }
 

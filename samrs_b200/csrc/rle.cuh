@@ -1,0 +1,161 @@
+// Instance payload on the device: uncompressed COCO run-length encoding + area of every mask of a tile.
+//
+// Replaces, per mask, the driver's D2H of a 1 MiB bool mask followed by `maskUtils.encode(np.asfortranarray(mask))`
+// and `np.sum(mask)` (Generate Dataset/main_sam_hbox_semantic.py:200-203).  The run semantics are the ones the
+// reference pins in-repo (segment_anything/utils/amg.py:107-135, mask_to_rle_pytorch): pixels in column-major
+// (Fortran) order, alternating run lengths starting with a run of zeros - a mask whose first pixel is set gets a
+// leading 0 - and the lengths sum to H*W.
+//
+// Three passes of integer / bit work, all HBM- or latency-bound (no tensor cores):
+//   1. pack: every thread owns one column x and 32 rows: packed[b][wy][x] bit r = mask[b][32 wy + r][x].  Loads are
+//      coalesced along x (row-major source), the stores of consecutive threads are consecutive words.  The fused
+//      variant computes the bits straight from the 256x256 low-res logits with the same explicitly rounded
+//      bilinear arithmetic as upsample4_threshold_kernel, so the 1 MiB/mask bool tensor is never materialised.
+//   2. count: one CTA per mask walks the packed words in column-major order (thread t owns a contiguous range of
+//      columns); transitions of a word are  w ^ ((w << 1) | carry)  with the carry taken from the previous pixel in
+//      Fortran order (the last row of the previous column; 0 before the first pixel); popcounts give the number of
+//      runs and the area.  A one-thread scan over the B masks turns run counts into offsets.
+//   3. emit: the same walk again; a block-wide exclusive scan gives every thread the rank of its first transition and
+//      the position of the last transition before it, so run k is written as position_k - position_{k-1}.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace samrs {
+
+// bits of column x, rows 32*wy .. 32*wy+31 of a row-major u8 mask (non-zero = set); rows >= H read as 0
+__global__ void rle_pack_kernel(const uint8_t* __restrict__ masks, int H, int W, int HW32, uint32_t* __restrict__ packed) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int wy = blockIdx.y, b = blockIdx.z;
+  if (x >= W) return;
+  const uint8_t* m = masks + (size_t(b) * H + size_t(wy) * 32) * W + x;
+  const int nr = min(32, H - wy * 32);
+  uint32_t w = 0;
+#pragma unroll 8
+  for (int r = 0; r < nr; ++r) w |= (m[size_t(r) * W] != 0 ? 1u : 0u) << r;
+  packed[(size_t(b) * HW32 + wy) * W + x] = w;
+}
+
+// same bits from the low-res logits of a 1024x1024 tile: bit = (bilinear x4 upsample > 0), arithmetic of simt.cuh bilerp
+__global__ void rle_pack_lowres_kernel(const float* __restrict__ low /*[B][256][256]*/, uint32_t* __restrict__ packed /*[B][32][1024]*/) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int wy = blockIdx.y, b = blockIdx.z;
+  if (x >= 1024) return;
+  const float* a = low + size_t(b) * 65536;
+  int x0, x1;
+  float lx0, lx1;
+  src_index_x4(x, 256, x0, x1, lx0, lx1);
+  uint32_t w = 0;
+#pragma unroll 4
+  for (int r = 0; r < 32; ++r) {
+    int y0, y1;
+    float ly0, ly1;
+    src_index_x4(wy * 32 + r, 256, y0, y1, ly0, ly1);
+    w |= (bilerp(a, y0, y1, ly0, ly1, x0, x1, lx0, lx1) > 0.0f ? 1u : 0u) << r;
+  }
+  packed[(size_t(b) * 32 + wy) * 1024 + x] = w;
+}
+
+constexpr int RLE_THREADS = 1024;
+
+// transitions of one packed word; `carry` = value of the previous pixel in Fortran order
+__device__ __forceinline__ uint32_t rle_transitions(uint32_t w, uint32_t valid, uint32_t carry) {
+  return (w ^ ((w << 1) | carry)) & valid;
+}
+
+// pass 2 (emit == false): runs[b] = transitions + 1, area[b];  pass 3 (emit == true): counts written at offsets[b]
+template <bool EMIT>
+__global__ void __launch_bounds__(RLE_THREADS) rle_scan_kernel(const uint32_t* __restrict__ packed, int H, int W, int HW32,
+                                                               long long* __restrict__ runs, long long* __restrict__ area,
+                                                               const long long* __restrict__ offsets, uint32_t* __restrict__ counts,
+                                                               long long capacity) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  const uint32_t* pk = packed + size_t(b) * HW32 * W;
+  const int cpt = (W + RLE_THREADS - 1) / RLE_THREADS;            // columns per thread, contiguous in Fortran order
+  const int xa = min(W, t * cpt), xb = min(W, xa + cpt);
+  const int last_bits = H - (HW32 - 1) * 32;                       // valid rows of a column's last word (1..32)
+  const uint32_t last_valid = last_bits == 32 ? 0xFFFFFFFFu : ((1u << last_bits) - 1u);
+
+  auto walk = [&](auto&& on_word) {
+    if (xa >= xb) return;
+    uint32_t carry = 0;
+    if (xa > 0) carry = (pk[size_t(HW32 - 1) * W + (xa - 1)] >> (last_bits - 1)) & 1u;
+    for (int x = xa; x < xb; ++x)
+      for (int wy = 0; wy < HW32; ++wy) {
+        const uint32_t valid = (wy == HW32 - 1) ? last_valid : 0xFFFFFFFFu;
+        const uint32_t w = pk[size_t(wy) * W + x] & valid;
+        on_word(x, wy, w, rle_transitions(w, valid, carry));
+        carry = (w >> ((wy == HW32 - 1 ? last_bits : 32) - 1)) & 1u;
+      }
+  };
+
+  // per-thread totals
+  unsigned long long n_tr = 0, n_set = 0;
+  long long last_pos = -1;
+  walk([&](int x, int wy, uint32_t w, uint32_t tr) {
+    n_tr += __popc(tr);
+    n_set += __popc(w);
+    if (tr) last_pos = (long long)x * H + wy * 32 + (31 - __clz(tr));
+  });
+
+  // block-wide exclusive scans: sum of transitions, max of last positions (and the total area)
+  __shared__ unsigned long long s_sum[RLE_THREADS / 32], s_area[RLE_THREADS / 32];
+  __shared__ long long s_max[RLE_THREADS / 32];
+  const int lane = t & 31, warp = t >> 5;
+  unsigned long long inc = n_tr, ar = n_set;
+  long long mx = last_pos;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long u = __shfl_up_sync(0xffffffffu, inc, o);
+    const long long m = __shfl_up_sync(0xffffffffu, mx, o);
+    if (lane >= o) { inc += u; mx = max(mx, m); }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ar += __shfl_xor_sync(0xffffffffu, ar, o);
+  if (lane == 31) { s_sum[warp] = inc; s_max[warp] = mx; }
+  if (lane == 0) s_area[warp] = ar;
+  __syncthreads();
+  unsigned long long base = 0, total = 0, area_total = 0;
+  long long prev_max = -1, max_total = -1;
+  for (int i = 0; i < RLE_THREADS / 32; ++i) {
+    if (i < warp) { base += s_sum[i]; prev_max = max(prev_max, s_max[i]); }
+    total += s_sum[i];
+    area_total += s_area[i];
+    max_total = max(max_total, s_max[i]);
+  }
+  const unsigned long long rank0 = base + inc - n_tr;             // transitions before this thread
+  long long prev = __shfl_up_sync(0xffffffffu, mx, 1);            // last transition position before this thread
+  prev = (lane == 0) ? prev_max : max(prev, prev_max);
+
+  if (!EMIT) {
+    if (t == 0) { runs[b] = (long long)total + 1; area[b] = (long long)area_total; }
+    return;
+  }
+  const long long off = offsets[b];
+  unsigned long long rank = rank0;
+  long long pp = prev < 0 ? 0 : prev;                             // run 0 is measured from pixel 0
+  walk([&](int x, int wy, uint32_t w, uint32_t tr) {
+    while (tr) {
+      const int bit = __ffs(tr) - 1;
+      tr &= tr - 1;
+      const long long p = (long long)x * H + wy * 32 + bit;
+      if (off + (long long)rank < capacity) counts[off + rank] = uint32_t(p - pp);
+      pp = p;
+      ++rank;
+    }
+  });
+  if (t == 0) {                                                    // final run: from the last transition to H*W
+    const long long lastp = max_total < 0 ? 0 : max_total;
+    if (off + (long long)total < capacity) counts[off + total] = uint32_t((long long)H * W - lastp);
+  }
+}
+
+__global__ void rle_offsets_kernel(const long long* __restrict__ runs, int B, long long* __restrict__ offsets) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    long long acc = 0;
+    for (int b = 0; b < B; ++b) { offsets[b] = acc; acc += runs[b]; }
+    offsets[B] = acc;
+  }
+}
+
+}  // namespace samrs

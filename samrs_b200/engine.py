@@ -28,6 +28,7 @@ ABI = {
     "samrs_decode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "samrs_postprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "samrs_semantic_reduce": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    "samrs_rle_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, ctypes.c_longlong, _vp, _vp, _vp]),
     "samrs_profile": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _i]),
     "samrs_launch_count": (_i, [_vp, _i64p]),
     "samrs_last_error": (ctypes.c_char_p, [_vp]),
@@ -185,6 +186,40 @@ class Engine:
             self._check(self._lib.samrs_semantic_reduce(self._h, low.data_ptr(), ids.data_ptr(), B, label_map.data_ptr(),
                                                         label_map.shape[0], label_map.shape[1], _stream(self.device)), "semantic_reduce")
         return label_map
+
+    def rle_encode(self, masks: Optional[torch.Tensor] = None, low_res: Optional[torch.Tensor] = None, capacity: Optional[int] = None):
+        """Uncompressed COCO RLE + area of B masks on the device (the driver's `maskUtils.encode` / `np.sum`,
+        main_sam_hbox_semantic.py:200-203, at the run level pinned by amg.py:107-135).
+
+        Pass `masks` (B,[1,]H,W) bool / uint8, or `low_res` (B,[1,]256,256) logits of a 1024x1024 tile (fused upsample +
+        threshold, no mask tensor).  Returns `(counts int32[capacity], offsets int64[B+1], area int64[B])` as CUDA
+        tensors, asynchronously; mask b's runs are `counts[offsets[b]:offsets[b+1]]`.  If `offsets[B] > capacity` the
+        tail was not written: call again with a larger capacity (`samrs_b200.rle.to_rle_dicts` checks this)."""
+        if (masks is None) == (low_res is None):
+            raise ValueError("rle_encode: pass either masks or low_res")
+        if masks is not None:
+            m = masks
+            if m.dtype == torch.bool:
+                m = m.view(torch.uint8)
+            m = self._dev(m, torch.uint8)
+            if m.dim() == 4:
+                m = m.reshape(m.shape[0] * m.shape[1], m.shape[2], m.shape[3])
+            B, H, W = m.shape
+            src_m, src_l = m.data_ptr(), None
+        else:
+            low = self._dev(low_res, torch.float32)
+            low = low.reshape(-1, 256, 256)
+            B, H, W = low.shape[0], 1024, 1024
+            src_m, src_l = None, low.data_ptr()
+        if capacity is None:
+            capacity = max(1, B) * 16384
+        counts = torch.empty((max(1, capacity),), dtype=torch.int32, device=self.device)
+        offsets = torch.empty((B + 1,), dtype=torch.int64, device=self.device)
+        area = torch.empty((max(1, B),), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_rle_encode(self._h, src_m, src_l, B, H, W, counts.data_ptr(), int(capacity),
+                                                   offsets.data_ptr(), area.data_ptr(), _stream(self.device)), "rle_encode")
+        return counts, offsets, area[:B]
 
     PROFILE_CATEGORIES = ("gemm_tc", "attn_window", "attn_global", "relpos", "layernorm", "encode_total", "decode_total", "epilogue")
 
