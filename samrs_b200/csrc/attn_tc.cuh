@@ -34,6 +34,7 @@ struct AttnParams {
   int num_qtiles;       // windowed: 25 windows * 2 halves; global: 32
   float scale_log2e;    // hd^-0.5 * log2(e)
   unsigned long long* dbg;   // optional pipeline trace of CTA 0 (tools/attn_trace.py)
+  int pv_split;         // attention v2, head dim 80: 1 = issue P.V as an N=64 and an N=16 MMA per k-step (first version), 0 = one N=80 MMA
 };
 __device__ __forceinline__ void attn_dbg(const AttnParams& p, int slot) {
   if (p.dbg != nullptr && blockIdx.x == 0 && slot < 4096) p.dbg[slot] = clock64();

@@ -224,6 +224,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_s = umma_idesc_f16(128, SN, 0, 0);
       constexpr uint32_t idesc_o64 = umma_idesc_f16(128, 64, 0, 1);
       constexpr uint32_t idesc_o16 = umma_idesc_f16(128, 16, 0, 1);
+      constexpr uint32_t idesc_o80 = umma_idesc_f16(128, 80, 0, 1);
       uint32_t qph = 0, kst = 0, kph = 0, vst = 0, vph = 0, pph[2] = {0, 0}, fph[2] = {0, 0}, rph = 0;
       const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aE = smem_u32(sE);
       auto issue_s = [&](int w) {                       // S_w = Q_w K^T into warpgroup w's columns
@@ -251,8 +252,14 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           for (int k = 0; k < SN / 16; ++k) {
             const uint32_t b = aV + vst * C::KV_BYTES + k * 2048;
             const uint32_t acc = (j > 0 || k > 0) ? 1u : 0u;
-            tc_mma_f16_ts(d, pa + uint32_t(k * 8), umma_desc_sw128(b), idesc_o64, acc);
-            if (NATOM == 2) tc_mma_f16_ts(d + 64, pa + uint32_t(k * 8), umma_desc_sw128(b + C::KV_ATOM_BYTES), idesc_o16, acc);
+            if (NATOM == 2 && !p.pv_split) {
+              // head dim 80 = one 64-wide swizzle atom + 16 columns of the next: a single N=80 MMA whose descriptor strides
+              // over the two atoms (LBO), instead of an N=64 and an N=16 MMA - the issue count, not the flops, bounds PV
+              tc_mma_f16_ts(d, pa + uint32_t(k * 8), umma_desc_sw128_mn(b, C::KV_ATOM_BYTES), idesc_o80, acc);
+            } else {
+              tc_mma_f16_ts(d, pa + uint32_t(k * 8), umma_desc_sw128(b), idesc_o64, acc);
+              if (NATOM == 2) tc_mma_f16_ts(d + 64, pa + uint32_t(k * 8), umma_desc_sw128(b + C::KV_ATOM_BYTES), idesc_o16, acc);
+            }
           }
         }
         __syncwarp();

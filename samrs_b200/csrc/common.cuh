@@ -267,6 +267,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   d |= uint64_t(2) << 61;               // SWIZZLE_128B
   return d;
 }
+// MN-major SW128 operand wider than one 64-element swizzle atom: `lbo_bytes` is the distance between consecutive
+// 64-element chunks along M/N (cute UMMA canonical layout ((64,m),(8,k)) : ((1,LBO),(64,SBO)))
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+  d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= uint64_t(1024 >> 4) << 32;
+  d |= uint64_t(1) << 46;
+  d |= uint64_t(2) << 61;
+  return d;
+}
 // Instruction descriptor for kind::f16 (cute::UMMA::InstrDescriptor): fp16 A/B, fp32 D.
 __host__ __device__ constexpr uint32_t umma_idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
   return (1u << 4)                      // D format F32

@@ -492,6 +492,8 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
   p.heads = e->heads;
   p.scale_log2e = (1.0f / sqrtf(float(hd))) * 1.4426950408889634f;
   p.dbg = static_cast<unsigned long long*>(g_attn_dbg);
+  static const bool pv_split = getenv("SAMRS_ATTN_PV_SPLIT") != nullptr;
+  p.pv_split = pv_split ? 1 : 0;
   CUtensorMap tQ, tKV;
   const uint64_t pitch_x = uint64_t(3 * D) * 2, pitch_y = pitch_x * 64;
   static const bool attn_v1 = getenv("SAMRS_ATTN_V1") != nullptr;     // first-generation kernel (one query tile per CTA)
@@ -1217,7 +1219,7 @@ int samrs_rle_encode(void* engine, const uint8_t* masks, const float* lowres, in
   LaunchScope ls(e);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (B < 0 || H < 1 || W < 1) return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_encode: bad shape"));
-  if ((masks == nullptr) == (lowres == nullptr))
+  if (B > 0 && (masks == nullptr) == (lowres == nullptr))
     return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_encode: pass either bool masks or low-res logits"));
   if (lowres != nullptr && (H != 1024 || W != 1024))
     return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_encode: the fused low-res path needs a 1024x1024 tile (pass masks otherwise)"));

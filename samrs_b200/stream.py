@@ -79,3 +79,28 @@ def semantic_tile(predictor, engine, image: np.ndarray, boxes: torch.Tensor, lab
         _, _, low = predictor.predict_torch(None, None, boxes=tb, mask_input=None, multimask_output=False)
         engine.semantic_reduce(low, labels[s:s + chunk], canvas)
     return canvas
+
+
+def instance_tile(predictor, engine, image: np.ndarray, boxes: torch.Tensor, labels, categories=None, chunk: int = 20):
+    """The instance branch of the same loop (`main_sam_hbox_semantic.py:183-204`): per box a COCO-RLE mask, its area and the
+    annotation fields.  The masks never leave the device: every chunk's low-res logits go through `Engine.rle_encode`
+    (fused upsample + threshold + run-length encoding), and only the runs (tens of KiB per tile) are copied back."""
+    from . import rle as host_rle
+    if image.shape[0] != 1024 or image.shape[1] != 1024:
+        raise ValueError("instance_tile: the fused low-res path needs a 1024x1024 tile")
+    predictor.set_image(image)
+    records = []
+    for s in range(0, boxes.shape[0], chunk):
+        tb = predictor.transform.apply_boxes_torch(boxes[s:s + chunk], image.shape[:2])
+        _, _, low = predictor.predict_torch(None, None, boxes=tb, mask_input=None, multimask_output=False)
+        n = low.shape[0]
+        cap = n * 16384
+        while True:
+            counts, offsets, area = engine.rle_encode(low_res=low, capacity=cap)
+            total = int(offsets[-1])                     # synchronises: the host needs the payload anyway
+            if total <= cap:
+                break
+            cap = total
+        records += host_rle.instance_records(counts, offsets, area, 1024, 1024, boxes[s:s + chunk].detach().cpu().numpy(),
+                                             [int(v) for v in labels[s:s + chunk]], categories)
+    return records

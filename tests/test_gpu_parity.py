@@ -176,6 +176,15 @@ def test_dropin_predictor_surface(tmp_path):
         assert np.abs(low.cpu().numpy()[:, :, ::2, ::2] - z["low_sub"]).max() < LOGIT_TOL
         sam_masks = masks.squeeze(1).cpu().numpy()
         assert sam_masks.shape == (2, 1024, 1024)
+        # instance branch (main_sam_hbox_semantic.py:200-204): fused on-device RLE == encoding the driver's host masks
+        from oracle import rle_oracle
+        from samrs_b200 import rle as host_rle
+        from samrs_b200.stream import instance_tile
+        recs = instance_tile(predictor, sam.engine, img, boxes, [3, 5], categories=[str(i) for i in range(18)], chunk=20)
+        assert len(recs) == 2 and recs[1]["label"] == 5 and recs[1]["category"] == "5"
+        for j, r in enumerate(recs):
+            assert r["size"] == int(sam_masks[j].sum())
+            assert host_rle.coco_string_decode(r["mask"]["counts"]) == rle_oracle.mask_to_rle(sam_masks[j])
     finally:
         sys.path.remove(samrs_b200.DROPIN_PATH)
         for k in [k for k in sys.modules if k == "segment_anything" or k.startswith("segment_anything.")]:
