@@ -343,6 +343,7 @@ struct Engine {
   uint32_t* rle_packed = nullptr;      // run-length encoder scratch: column-major bit planes [B][ceil(H/32)][W]
   size_t rle_packed_words = 0;
   long long* rle_runs = nullptr;       // [rle_runs_cap] runs per mask
+  long long* rle_tstate = nullptr;     // [rle_runs_cap][1024][2] per-thread (transitions, last position) of the count pass
   int rle_runs_cap = 0;
   float* splitk_ws = nullptr;          // split-K partial sums of the token-side SGEMMs
   size_t splitk_ws_floats = 0;
@@ -1235,6 +1236,7 @@ int samrs_rle_encode(void* engine, const uint8_t* masks, const float* lowres, in
   }
   if (B + 1 > e->rle_runs_cap) {
     if (e->alloc(&e->rle_runs, size_t(B) + 1) != 0) return set_err(e, 1);
+    if (e->alloc(&e->rle_tstate, (size_t(B) + 1) * RLE_THREADS * 2) != 0) return set_err(e, 1);
     e->rle_runs_cap = B + 1;
   }
   if (B > 0) {
@@ -1243,10 +1245,10 @@ int samrs_rle_encode(void* engine, const uint8_t* masks, const float* lowres, in
       if (masks) rle_pack_kernel<<<dim3((W + 127) / 128, HW32, nb), 128, 0, st>>>(masks + size_t(b0) * H * W, H, W, HW32, e->rle_packed + size_t(b0) * HW32 * W);
       else rle_pack_lowres_kernel<<<dim3(8, 32, nb), 128, 0, st>>>(lowres + size_t(b0) * 65536, e->rle_packed + size_t(b0) * HW32 * W);
     }
-    rle_scan_kernel<false><<<B, RLE_THREADS, 0, st>>>(e->rle_packed, H, W, HW32, e->rle_runs, area_out, nullptr, nullptr, 0);
+    rle_scan_kernel<false><<<B, RLE_THREADS, 0, st>>>(e->rle_packed, H, W, HW32, e->rle_runs, area_out, nullptr, nullptr, 0, e->rle_tstate);
   }
   rle_offsets_kernel<<<1, 32, 0, st>>>(e->rle_runs, B, offsets_out);
-  if (B > 0) rle_scan_kernel<true><<<B, RLE_THREADS, 0, st>>>(e->rle_packed, H, W, HW32, nullptr, nullptr, offsets_out, counts_out, capacity);
+  if (B > 0) rle_scan_kernel<true><<<B, RLE_THREADS, 0, st>>>(e->rle_packed, H, W, HW32, nullptr, nullptr, offsets_out, counts_out, capacity, e->rle_tstate);
   count_launch(B > 0 ? 4 : 1);
   if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_encode launch failed"));
   return 0;

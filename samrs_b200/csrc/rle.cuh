@@ -36,7 +36,11 @@ __global__ void rle_pack_kernel(const uint8_t* __restrict__ masks, int H, int W,
   packed[(size_t(b) * HW32 + wy) * W + x] = w;
 }
 
-// same bits from the low-res logits of a 1024x1024 tile: bit = (bilinear x4 upsample > 0), arithmetic of simt.cuh bilerp
+// same bits from the low-res logits of a 1024x1024 tile: bit = (bilinear x4 upsample > 0), arithmetic of simt.cuh bilerp.
+// The 32 output rows of a word touch low-res rows 8 wy - 1 .. 8 wy + 8 only, so the horizontal interpolation
+// r(j) = lx0 a[j][x0] + lx1 a[j][x1] is evaluated once per low-res row (10 instead of 64 times) and reused; the values and
+// the order of the roundings are those of bilerp(), so the bits equal upsample4_threshold_kernel's.  Rows clamped at the
+// borders carry weight 0 (top) or duplicate row 255 (bottom), exactly as ATen's index clamp does.
 __global__ void rle_pack_lowres_kernel(const float* __restrict__ low /*[B][256][256]*/, uint32_t* __restrict__ packed /*[B][32][1024]*/) {
   const int x = blockIdx.x * blockDim.x + threadIdx.x;
   const int wy = blockIdx.y, b = blockIdx.z;
@@ -45,13 +49,21 @@ __global__ void rle_pack_lowres_kernel(const float* __restrict__ low /*[B][256][
   int x0, x1;
   float lx0, lx1;
   src_index_x4(x, 256, x0, x1, lx0, lx1);
+  float hrow[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    const int j = min(max(8 * wy - 1 + k, 0), 255);
+    hrow[k] = __fadd_rn(__fmul_rn(lx0, a[j * 256 + x0]), __fmul_rn(lx1, a[j * 256 + x1]));
+  }
   uint32_t w = 0;
-#pragma unroll 4
+#pragma unroll
   for (int r = 0; r < 32; ++r) {
     int y0, y1;
     float ly0, ly1;
-    src_index_x4(wy * 32 + r, 256, y0, y1, ly0, ly1);
-    w |= (bilerp(a, y0, y1, ly0, ly1, x0, x1, lx0, lx1) > 0.0f ? 1u : 0u) << r;
+    src_index_x4(wy * 32 + r, 256, y0, y1, ly0, ly1);                 // only the weights are used; the rows are hrow[i0], hrow[i0 + 1]
+    const int i0 = (r >> 2) + ((r & 3) >= 2 ? 1 : 0);
+    const float v = __fadd_rn(__fmul_rn(ly0, hrow[i0]), __fmul_rn(ly1, hrow[i0 + 1]));
+    w |= (v > 0.0f ? 1u : 0u) << r;
   }
   packed[(size_t(b) * 32 + wy) * 1024 + x] = w;
 }
@@ -68,7 +80,7 @@ template <bool EMIT>
 __global__ void __launch_bounds__(RLE_THREADS) rle_scan_kernel(const uint32_t* __restrict__ packed, int H, int W, int HW32,
                                                                long long* __restrict__ runs, long long* __restrict__ area,
                                                                const long long* __restrict__ offsets, uint32_t* __restrict__ counts,
-                                                               long long capacity) {
+                                                               long long capacity, long long* __restrict__ tstate /*[B][1024][2]*/) {
   const int b = blockIdx.x, t = threadIdx.x;
   const uint32_t* pk = packed + size_t(b) * HW32 * W;
   const int cpt = (W + RLE_THREADS - 1) / RLE_THREADS;            // columns per thread, contiguous in Fortran order
@@ -76,39 +88,39 @@ __global__ void __launch_bounds__(RLE_THREADS) rle_scan_kernel(const uint32_t* _
   const int last_bits = H - (HW32 - 1) * 32;                       // valid rows of a column's last word (1..32)
   const uint32_t last_valid = last_bits == 32 ? 0xFFFFFFFFu : ((1u << last_bits) - 1u);
 
-  // column-major walk over this thread's words.  The words of a column are fetched 32 at a time with independent loads
-  // (one round trip to L2 instead of 32 dependent ones: with one CTA per mask the walk is latency-, not bandwidth-bound)
+  // column-major walk over this thread's words
   auto walk = [&](auto&& on_word) {
     if (xa >= xb) return;
     uint32_t carry = 0;
     if (xa > 0) carry = (pk[size_t(HW32 - 1) * W + (xa - 1)] >> (last_bits - 1)) & 1u;
-    for (int x = xa; x < xb; ++x)
-      for (int w0 = 0; w0 < HW32; w0 += 32) {
-        uint32_t wd[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) wd[i] = (w0 + i < HW32) ? pk[size_t(w0 + i) * W + x] : 0u;
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          const int wy = w0 + i;
-          if (wy < HW32) {
-            const bool lastw = (wy == HW32 - 1);
-            const uint32_t valid = lastw ? last_valid : 0xFFFFFFFFu;
-            const uint32_t w = wd[i] & valid;
-            on_word(x, wy, w, rle_transitions(w, valid, carry));
-            carry = (w >> ((lastw ? last_bits : 32) - 1)) & 1u;
-          }
-        }
+    for (int x = xa; x < xb; ++x) {
+#pragma unroll 8
+      for (int wy = 0; wy < HW32; ++wy) {
+        const bool lastw = (wy == HW32 - 1);
+        const uint32_t valid = lastw ? last_valid : 0xFFFFFFFFu;
+        const uint32_t w = pk[size_t(wy) * W + x] & valid;
+        on_word(x, wy, w, rle_transitions(w, valid, carry));
+        carry = (w >> ((lastw ? last_bits : 32) - 1)) & 1u;
       }
+    }
   };
 
-  // per-thread totals
+  // per-thread totals: computed by the count pass and kept in `tstate` for the emit pass
   unsigned long long n_tr = 0, n_set = 0;
   long long last_pos = -1;
-  walk([&](int x, int wy, uint32_t w, uint32_t tr) {
-    n_tr += __popc(tr);
-    n_set += __popc(w);
-    if (tr) last_pos = (long long)x * H + wy * 32 + (31 - __clz(tr));
-  });
+  long long* ts = tstate + (size_t(b) * RLE_THREADS + t) * 2;
+  if (!EMIT) {
+    walk([&](int x, int wy, uint32_t w, uint32_t tr) {
+      n_tr += __popc(tr);
+      n_set += __popc(w);
+      if (tr) last_pos = (long long)x * H + wy * 32 + (31 - __clz(tr));
+    });
+    ts[0] = (long long)n_tr;
+    ts[1] = last_pos;
+  } else {
+    n_tr = (unsigned long long)ts[0];
+    last_pos = ts[1];
+  }
 
   // block-wide exclusive scans: sum of transitions, max of last positions (and the total area)
   __shared__ unsigned long long s_sum[RLE_THREADS / 32], s_area[RLE_THREADS / 32];

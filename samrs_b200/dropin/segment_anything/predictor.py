@@ -23,7 +23,10 @@ class SamPredictor:
         if image_format != self.model.image_format:
             image = image[..., ::-1]
         input_image = self.transform.apply_image(image)
-        input_image_torch = torch.as_tensor(np.ascontiguousarray(input_image), device=self.device)
+        # H2D: asynchronous when the caller's array lives in pinned host memory (the copy is then ordered on the current
+        # stream like every other call of this class), the reference's blocking copy otherwise
+        host = torch.from_numpy(np.ascontiguousarray(input_image))
+        input_image_torch = host.to(self.device, non_blocking=host.is_pinned())
         # the engine reads HWC uint8 directly; the permute of the reference is a layout detail of its conv
         self._set_device_image(input_image_torch, hwc=True, original_image_size=image.shape[:2])
 

@@ -24,6 +24,7 @@ def step():
     low, _ = eng.decode(boxes=boxes, multimask_output=False)
     eng.postprocess(low, (1024, 1024), (1024, 1024))
     eng.semantic_reduce(low, labels, canvas)
+    eng.rle_encode(low_res=low, capacity=1 << 20)
 
 
 step()
