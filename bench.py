@@ -221,12 +221,21 @@ def run_ours(args):
     labels_d = [l.to(device) for l in labels_h]
     canvases = [torch.empty((1024, 1024), dtype=torch.uint8, device=device) for _ in range(NS)]
 
+    VARIANT_STEP = os.environ.get("SAMRS_BENCH_STEP", "")     # diagnostics only; the reported line uses the default
+
     def step_resident(i):
         nonlocal NS
         j, k = i % N_TILES, i % NS
         en, canvas = engines[k], canvases[k]
         with torch.cuda.stream(streams[k]):
             en.encode(tiles_d[j])
+            if VARIANT_STEP == "chunks":             # diagnostic: the driver's 20 + 12 chunking on resident inputs
+                canvas.fill_(255)
+                for s in range(0, BOXES, CHUNK):
+                    low, _ = en.decode(boxes=boxes_d[j][s:s + CHUNK], multimask_output=False)
+                    en.postprocess(low, (1024, 1024), (1024, 1024))
+                    en.semantic_reduce(low, labels_d[j][s:s + CHUNK], canvas)
+                return
             low, _ = en.decode(boxes=boxes_d[j], multimask_output=False)
             en.postprocess(low, (1024, 1024), (1024, 1024))
             canvas.fill_(255)
