@@ -1,10 +1,10 @@
 // CTA-pair (cta_group::2) variant of the tcgen05 GEMM: two SMs of one TPC cooperate on a 256 x BN output tile.
 //
-// Why: with one CTA per 128 x BN tile every SM pulls (128 + BN) x 64 fp16 from L2 per 128 x BN x 64 MMA block,
-// which at BN <= 256 exceeds the ~50 B/clk/SM the L2 can deliver and capped the 1-CTA kernel at ~45 % tensor-pipe
-// utilisation (profiles/r01_*).  In a pair each CTA loads its own 128 rows of A and only HALF of the B tile; the
-// MMA (M = 256, issued by the leader CTA) reads both halves of B from the two CTAs' shared memory, so the bytes
-// per flop halve.  Accumulators stay per-CTA: each CTA's TMEM holds its 128 rows x BN columns and each CTA runs
+// Why: with one CTA per 128 x BN tile every SM pulls (128 + BN) x 64 fp16 from L2 per 128 x BN x 64 MMA block; once the
+// issue loop was tight (profiles/r01_gemm_trace_v5.txt) that feed bounded the 1-CTA kernel.  In a pair each CTA loads its
+// own 128 rows of A and only HALF of the B tile; the MMA (M = 256, issued by the leader CTA) reads both halves of B from
+// the two CTAs' shared memory, so the B bytes per flop halve and the main loop runs at the MMA floor (335-340 clk per
+// 64-deep k-block of a 160-wide tile, floor 320).  Accumulators stay per-CTA: each CTA's TMEM holds its 128 rows x BN columns and each CTA runs
 // its own epilogue warps.
 //
 // Protocol (leader = cluster rank 0):
