@@ -62,7 +62,8 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // exp2 on the FMA / integer pipes (Cody-Waite split + degree-4 polynomial on [-0.5, 0.5], relative error 3.6e-6, far
 // below the fp16 rounding of P).  The MUFU unit retires one warp-wide ex2 per 8 clocks per SM sub-partition and the
 // windowed softmax was bound by it (and by the fp32->fp16 packs that share it): every third exponential of the
-// windowed kernel goes here (the global kernel measured slightly slower with it and keeps MUFU only).
+// windowed kernel goes here.  The global kernel is issue-bound instead: with every 3rd / 4th exponential on the FMA pipe it
+// ran 13 % / 7 % slower (tools/gpu_ab.sh, -DSAMRS_GLOBAL_POLY_DIV=3|4), so it keeps MUFU only.
 __device__ __forceinline__ float ex2_poly(float x) {
   x = fmaxf(x, -125.0f);
   const float r = x + 12582912.0f;                 // 1.5 * 2^23: the integer part of x lands in the low mantissa bits
@@ -73,9 +74,13 @@ __device__ __forceinline__ float ex2_poly(float x) {
   q = fmaf(q, f, 1.0000001f);
   return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
 }
-template <int I, bool POLY>
+// DIV = 0: MUFU only; DIV = n: every n-th exponential goes to the FMA pipe
+#ifndef SAMRS_GLOBAL_POLY_DIV
+#define SAMRS_GLOBAL_POLY_DIV 0
+#endif
+template <int I, int DIV>
 __device__ __forceinline__ float ex2_mixed(float x) {
-  if constexpr (POLY && I % 3 == 2) return ex2_poly(x);
+  if constexpr (DIV > 0 && I % (DIV > 0 ? DIV : 1) == (DIV > 0 ? DIV : 1) - 1) return ex2_poly(x);
   else return ex2_approx(x);
 }
 
@@ -455,8 +460,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             constexpr int i = decltype(ic)::value;
             constexpr int c = c0 + i;
             float e0 = 0.f, e1 = 0.f;
-            if constexpr (c < KR) e0 = ex2_mixed<i, NKT == 1>(fmaf(__uint_as_float(v[i]), p.scale_log2e, dh[NKT > 1 ? c / BX : 0]));
-            if constexpr (c + 1 < KR) e1 = ex2_mixed<i + 1, NKT == 1>(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, dh[NKT > 1 ? (c + 1) / BX : 0]));
+            if constexpr (c < KR) e0 = ex2_mixed<i, (NKT == 1 ? 3 : SAMRS_GLOBAL_POLY_DIV)>(fmaf(__uint_as_float(v[i]), p.scale_log2e, dh[NKT > 1 ? c / BX : 0]));
+            if constexpr (c + 1 < KR) e1 = ex2_mixed<i + 1, (NKT == 1 ? 3 : SAMRS_GLOBAL_POLY_DIV)>(fmaf(__uint_as_float(v[i + 1]), p.scale_log2e, dh[NKT > 1 ? (c + 1) / BX : 0]));
             l_tile += e0 + e1;
             __half2 h = __floats2half2_rn(e0, e1);
             pk[i / 2] = *reinterpret_cast<uint32_t*>(&h);

@@ -15,7 +15,7 @@ import torch
 
 from .config import SamGeometry, geometry
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsamrs_b200.so")
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), os.environ.get("SAMRS_LIB", "libsamrs_b200.so"))   # SAMRS_LIB: A/B builds (tools)
 _lib: Optional[ctypes.CDLL] = None
 
 # name -> (restype, argtypes); must list every symbol declared in include/samrs_b200.h
