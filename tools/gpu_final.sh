@@ -1,0 +1,7 @@
+#!/bin/bash
+# final validation of a round: all GPU tests, smoke, the default bench line
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -3
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
+tail -2 gpurun_out/bench_final.err; cat gpurun_out/bench_final.json
