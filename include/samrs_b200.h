@@ -60,6 +60,12 @@ int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int i
 int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_ids, int B,
                           uint8_t* label_map_inout, int H, int W, void* stream);
 
+/* image resize of the predictor on the device: replaces ResizeLongestSide.apply_image
+ * -- segment_anything/utils/transforms.py:26-31 (torchvision resize of a PIL image == PIL.Image.resize(BILINEAR)).
+ * src (H,W,3) uint8 -> dst (out_h,out_w,3) uint8, both on the device, bit-identical to Pillow's two-pass 8-bit
+ * fixed-point resampler (horizontal pass first, 22-bit taps, triangle filter widened when shrinking). */
+int samrs_resize_bilinear_u8(void* engine, const uint8_t* src_hwc, int H, int W, uint8_t* dst_hwc, int out_h, int out_w, void* stream);
+
 /* instance payload on the device: uncompressed COCO run-length encoding and area of B masks.
  * Replaces, per mask, the D2H of the bool mask + `maskUtils.encode(np.asfortranarray(mask))` + `np.sum(mask)`
  * -- Generate Dataset/main_sam_hbox_semantic.py:200-203; run semantics as pinned in-repo by

@@ -340,6 +340,10 @@ struct Engine {
   // per-image decoder cache
   float *src0, *K0, *V0, *Qi0;
   float* pp_full = nullptr;            // postprocess scratch for non-1024 sizes
+  struct ResizeTab { int in, out, ksize; int* bounds; int* kk; };
+  std::vector<ResizeTab> resize_tabs;   // Pillow tap tables per (input size, output size), built on first use
+  uint8_t* resize_tmp = nullptr;       // horizontal-pass result [H][out_w][3]
+  size_t resize_tmp_bytes = 0;
   uint32_t* rle_packed = nullptr;      // run-length encoder scratch: column-major bit planes [B][ceil(H/32)][W]
   size_t rle_packed_words = 0;
   long long* rle_runs = nullptr;       // [rle_runs_cap] runs per mask
@@ -1209,6 +1213,93 @@ int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int i
     count_launch(2);
   }
   if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "postprocess launch failed"));
+  return 0;
+}
+
+// Pillow's precompute_coeffs + normalize_coeffs_8bpc for the bilinear (triangle) filter, in double as there
+static void pil_coeffs(int in_size, int out_size, std::vector<int>& bounds, std::vector<int>& kk, int& ksize) {
+  const double scale = double(in_size) / double(out_size);
+  const double filterscale = scale < 1.0 ? 1.0 : scale;
+  const double support = 1.0 * filterscale;
+  ksize = int(ceil(support)) * 2 + 1;
+  bounds.assign(size_t(out_size) * 2, 0);
+  kk.assign(size_t(out_size) * ksize, 0);
+  const double ss = 1.0 / filterscale;
+  std::vector<double> w(ksize);
+  for (int xx = 0; xx < out_size; ++xx) {
+    const double center = (xx + 0.5) * scale;
+    int xmin = int(center - support + 0.5);
+    if (xmin < 0) xmin = 0;
+    int xmax = int(center + support + 0.5);
+    if (xmax > in_size) xmax = in_size;
+    xmax -= xmin;
+    double ww = 0.0;
+    for (int x = 0; x < ksize; ++x) w[x] = 0.0;
+    for (int x = 0; x < xmax; ++x) {
+      double v = (x + xmin - center + 0.5) * ss;
+      if (v < 0.0) v = -v;
+      w[x] = v < 1.0 ? 1.0 - v : 0.0;
+      ww += w[x];
+    }
+    for (int x = 0; x < xmax; ++x)
+      if (ww != 0.0) w[x] /= ww;
+    for (int x = 0; x < ksize; ++x)
+      kk[size_t(xx) * ksize + x] = w[x] < 0 ? int(-0.5 + w[x] * double(1 << 22)) : int(0.5 + w[x] * double(1 << 22));
+    bounds[2 * xx] = xmin;
+    bounds[2 * xx + 1] = xmax;
+  }
+}
+
+static int resize_table(Engine* e, int in_size, int out_size, cudaStream_t st, const Engine::ResizeTab** out) {
+  for (const auto& t : e->resize_tabs)
+    if (t.in == in_size && t.out == out_size) { *out = &t; return 0; }
+  std::vector<int> b, k;
+  Engine::ResizeTab t{in_size, out_size, 0, nullptr, nullptr};
+  pil_coeffs(in_size, out_size, b, k, t.ksize);
+  if (e->alloc(&t.bounds, b.size()) != 0 || e->alloc(&t.kk, k.size()) != 0) return 1;
+  SAMRS_CUDA_OK(cudaMemcpyAsync(t.bounds, b.data(), b.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(t.kk, k.data(), k.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  SAMRS_CUDA_OK(cudaStreamSynchronize(st));          // the host vectors go out of scope; once per size pair
+  e->resize_tabs.push_back(t);
+  *out = &e->resize_tabs.back();
+  return 0;
+}
+
+int samrs_resize_bilinear_u8(void* engine, const uint8_t* src_hwc, int H, int W, uint8_t* dst_hwc, int out_h, int out_w, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (H < 1 || W < 1 || out_h < 1 || out_w < 1 || H > 32768 || W > 32768 || out_h > 32768 || out_w > 32768 || !src_hwc || !dst_hwc)
+    return set_err(e, samrs::fail(__FILE__, __LINE__, "resize: bad shape or null pointer"));
+  const uint8_t* cur = src_hwc;
+  if (out_w != W) {
+    const Engine::ResizeTab* th = nullptr;
+    if (resize_table(e, W, out_w, st, &th) != 0) return set_err(e, 1);
+    uint8_t* hdst = dst_hwc;
+    if (out_h != H) {                                   // a vertical pass follows: horizontal result goes to scratch
+      const size_t need = size_t(H) * out_w * 3;
+      if (need > e->resize_tmp_bytes) {
+        if (e->alloc(&e->resize_tmp, need) != 0) return set_err(e, 1);
+        e->resize_tmp_bytes = need;
+      }
+      hdst = e->resize_tmp;
+    }
+    pil_resize_h_kernel<<<dim3((out_w + 127) / 128, H), 128, 0, st>>>(cur, W, hdst, out_w, th->bounds, th->kk, th->ksize);
+    count_launch();
+    cur = hdst;
+  }
+  if (out_h != H) {
+    const Engine::ResizeTab* tv = nullptr;
+    if (resize_table(e, H, out_h, st, &tv) != 0) return set_err(e, 1);
+    const int row = out_w * 3;
+    pil_resize_v_kernel<<<dim3((row + 255) / 256, out_h), 256, 0, st>>>(cur, row, dst_hwc, tv->bounds, tv->kk, tv->ksize);
+    count_launch();
+  } else if (out_w == W) {
+    SAMRS_CUDA_OK(cudaMemcpyAsync(dst_hwc, src_hwc, size_t(H) * W * 3, cudaMemcpyDeviceToDevice, st));
+  }
+  if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "resize launch failed"));
   return 0;
 }
 

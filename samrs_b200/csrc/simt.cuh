@@ -953,6 +953,45 @@ __global__ void upsample4_paint_kernel(const float* __restrict__ low /*[NB][256]
   *reinterpret_cast<uint32_t*>(canvas + size_t(y) * 1024 + x4 * 4) = cur;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Pillow-exact 8-bit bilinear image resize (ResizeLongestSide.apply_image, SA/utils/transforms.py:26-31 ->
+// PIL.Image.resize(BILINEAR) -> libImaging/Resample.c): two separable passes over uint8 HWC data with 22-bit fixed-point
+// taps; each pass accumulates 2^21 + sum(pixel * tap) in int32, shifts by 22 and clamps to [0, 255]; the horizontal pass
+// runs first and its uint8 result feeds the vertical one.  Tap tables (first tap, count, weights) come from the host
+// (engine.cu pil_coeffs, double arithmetic as in Resample.c precompute_coeffs / normalize_coeffs_8bpc).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint8_t pil_clip8(int acc) { return uint8_t(min(max(acc >> 22, 0), 255)); }
+
+__global__ void pil_resize_h_kernel(const uint8_t* __restrict__ src /*[H][W][3]*/, int W, uint8_t* __restrict__ dst /*[H][W1][3]*/, int W1,
+                                    const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  const int x1 = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x1 >= W1) return;
+  const int lo = bounds[2 * x1], n = bounds[2 * x1 + 1];
+  const int* k = kk + size_t(x1) * ksize;
+  const uint8_t* p = src + (size_t(y) * W + lo) * 3;
+  int a0 = 1 << 21, a1 = 1 << 21, a2 = 1 << 21;
+  for (int i = 0; i < n; ++i) {
+    const int kv = k[i];
+    a0 += int(p[3 * i]) * kv;
+    a1 += int(p[3 * i + 1]) * kv;
+    a2 += int(p[3 * i + 2]) * kv;
+  }
+  uint8_t* o = dst + (size_t(y) * W1 + x1) * 3;
+  o[0] = pil_clip8(a0); o[1] = pil_clip8(a1); o[2] = pil_clip8(a2);
+}
+
+// vertical pass: one thread per byte of an output row (x * 3 + c), consecutive threads read consecutive bytes
+__global__ void pil_resize_v_kernel(const uint8_t* __restrict__ src /*[H][row]*/, int row_bytes, uint8_t* __restrict__ dst /*[H1][row]*/,
+                                    const int* __restrict__ bounds, const int* __restrict__ kk, int ksize) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x, y1 = blockIdx.y;
+  if (e >= row_bytes) return;
+  const int lo = bounds[2 * y1], n = bounds[2 * y1 + 1];
+  const int* k = kk + size_t(y1) * ksize;
+  int a = 1 << 21;
+  for (int i = 0; i < n; ++i) a += int(src[size_t(lo + i) * row_bytes + e]) * k[i];
+  dst[size_t(y1) * row_bytes + e] = pil_clip8(a);
+}
+
 // general bilinear resize (align_corners=False, ATen scale = in/out) of a cropped source view
 __global__ void bilinear_resize_kernel(const float* __restrict__ in, int in_ld, int in_plane, int in_h, int in_w,
                                        float* __restrict__ out_f, uint8_t* __restrict__ out_mask, int out_h, int out_w, int NB) {

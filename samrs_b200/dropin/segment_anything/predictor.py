@@ -22,11 +22,17 @@ class SamPredictor:
         assert image_format in ["RGB", "BGR"], f"image_format must be in ['RGB', 'BGR'], is {image_format}."
         if image_format != self.model.image_format:
             image = image[..., ::-1]
-        input_image = self.transform.apply_image(image)
+        # resize to long side 1024: identity for 1024-long tiles; otherwise the original pixels go to the device and
+        # `samrs_resize_bilinear_u8` reproduces PIL's resampler bit for bit (the reference does it on the host with PIL)
+        target = self.transform.get_preprocess_shape(image.shape[0], image.shape[1], self.transform.target_length)
         # H2D: asynchronous when the caller's array lives in pinned host memory (the copy is then ordered on the current
         # stream like every other call of this class), the reference's blocking copy otherwise
-        host = torch.from_numpy(np.ascontiguousarray(input_image))
+        host = torch.from_numpy(np.ascontiguousarray(image))
         input_image_torch = host.to(self.device, non_blocking=host.is_pinned())
+        if tuple(target) != tuple(image.shape[:2]):
+            if input_image_torch.dtype != torch.uint8 or input_image_torch.dim() != 3 or input_image_torch.shape[2] != 3:
+                raise NotImplementedError("samrs_b200 resizes 8-bit HWC RGB images; got " + str(tuple(image.shape)) + " " + str(image.dtype))
+            input_image_torch = self.model._require_engine().resize_image(input_image_torch, target)
         # the engine reads HWC uint8 directly; the permute of the reference is a layout detail of its conv
         self._set_device_image(input_image_torch, hwc=True, original_image_size=image.shape[:2])
 

@@ -28,6 +28,7 @@ ABI = {
     "samrs_decode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "samrs_postprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "samrs_semantic_reduce": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    "samrs_resize_bilinear_u8": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),
     "samrs_rle_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, ctypes.c_longlong, _vp, _vp, _vp]),
     "samrs_profile": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _i]),
     "samrs_launch_count": (_i, [_vp, _i64p]),
@@ -186,6 +187,19 @@ class Engine:
             self._check(self._lib.samrs_semantic_reduce(self._h, low.data_ptr(), ids.data_ptr(), B, label_map.data_ptr(),
                                                         label_map.shape[0], label_map.shape[1], _stream(self.device)), "semantic_reduce")
         return label_map
+
+    def resize_image(self, image: torch.Tensor, out_hw: Sequence[int]) -> torch.Tensor:
+        """(H,W,3) uint8 CUDA image -> (out_h,out_w,3) uint8, bit-identical to `PIL.Image.resize(..., BILINEAR)`
+        (the reference's `ResizeLongestSide.apply_image`, utils/transforms.py:26-31)."""
+        img = self._dev(image, torch.uint8)
+        if img.dim() != 3 or img.shape[2] != 3:
+            raise ValueError("resize_image expects an HWC uint8 image with 3 channels")
+        oh, ow = int(out_hw[0]), int(out_hw[1])
+        out = torch.empty((oh, ow, 3), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_resize_bilinear_u8(self._h, img.data_ptr(), img.shape[0], img.shape[1], out.data_ptr(), oh, ow,
+                                                           _stream(self.device)), "resize_image")
+        return out
 
     def rle_encode(self, masks: Optional[torch.Tensor] = None, low_res: Optional[torch.Tensor] = None, capacity: Optional[int] = None):
         """Uncompressed COCO RLE + area of B masks on the device (the driver's `maskUtils.encode` / `np.sum`,
