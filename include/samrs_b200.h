@@ -101,6 +101,13 @@ int samrs_test_attention(void* engine, const void* qkv, const float* rel_pos_h, 
 /* fp32 CUDA-core GEMM of the decoder: C = act(A W^T + bias), act 0 none / 1 relu / 2 gelu. */
 int samrs_test_sgemm(void* engine, const float* A, const float* W, float* C, const float* bias, int M, int N,
                      int K, int act, void* stream);
+/* pipeline instrumentation for tools/gemm_trace.py and tools/attn_trace.py (process-wide, not thread-safe):
+ * a device buffer of 4096 uint64 that CTA 0 of the next tensor-core GEMM / attention launches fills with clock64
+ * stamps (NULL switches tracing off), and the GEMM experiment mask (bit0 skip TMA loads, bit1 skip MMAs, bit2 skip
+ * the epilogue; results are garbage, timing only). */
+void samrs_test_set_gemm_trace(void* dev_buf);
+void samrs_test_set_gemm_mode(int mode);
+void samrs_test_set_attn_trace(void* dev_buf);
 
 #ifdef __cplusplus
 }

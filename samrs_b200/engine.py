@@ -37,6 +37,9 @@ ABI = {
     "samrs_test_gemm": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _i, _vp, _vp, _i, _i, _vp]),
     "samrs_test_attention": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp]),
     "samrs_test_sgemm": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
+    "samrs_test_set_gemm_trace": (None, [_vp]),
+    "samrs_test_set_gemm_mode": (None, [_i]),
+    "samrs_test_set_attn_trace": (None, [_vp]),
 }
 
 
