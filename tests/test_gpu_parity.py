@@ -95,6 +95,29 @@ def test_engine_matches_oracle_full_tensors(variant, kind):
     assert flips < 0.005 * m_ref.numel()
 
 
+def test_many_prompts_span_several_decoder_passes():
+    """BASELINE config 4 density and beyond: 64 tiny boxes (exactly one decoder pass) and 70 boxes (64 + 6: the engine
+    splits internally) against the oracle fed with the engine's own features; splitting must not change any prompt."""
+    from oracle import sam_oracle as O
+    variant = "vit_t64"
+    g, w = geometry(variant), synthetic_state_dict(variant, 0)
+    eng = engine_for(variant)
+    img = synth.tile(9)
+    feat = eng.encode(torch.from_numpy(img).cuda())
+    boxes = torch.from_numpy(np.concatenate([synth.hboxes(9, 64, tiny=True), synth.hboxes(10, 6)], 0))
+    low70, iou70 = eng.decode(boxes=boxes.cuda(), multimask_output=False)
+    low64, iou64 = eng.decode(boxes=boxes[:64].cuda(), multimask_output=False)
+    low6, iou6 = eng.decode(boxes=boxes[64:].cuda(), multimask_output=False)
+    torch.cuda.synchronize()
+    assert tuple(low70.shape) == (70, 1, 256, 256)
+    assert torch.equal(low70[:64], low64) and torch.equal(low70[64:], low6)
+    assert torch.equal(iou70[:64], iou64) and torch.equal(iou70[64:], iou6)
+    with torch.no_grad():
+        _, i_ref, l_ref = O.predict_torch(w, g, feat.cpu(), None, None, boxes, None, False)
+    assert (low70.cpu() - l_ref).abs().max().item() < LOGIT_TOL
+    assert (iou70.cpu() - i_ref).abs().max().item() < LOGIT_TOL
+
+
 def test_decoder_only_from_reference_features(golden_dir):
     """Isolates the fp32 decoder: feed the ORACLE's features, compare logits (decoder runs in fp32 -> tight)."""
     from oracle import sam_oracle as O
