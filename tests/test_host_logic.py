@@ -114,3 +114,27 @@ def test_resize_longest_side_matches_oracle_and_reference_rule():
         sys.path.remove(samrs_b200.DROPIN_PATH)
         for k in [k for k in sys.modules if k == "segment_anything" or k.startswith("segment_anything.")]:
             del sys.modules[k]
+
+
+def test_gelu_epilogue_polynomial_is_accurate():
+    """The GEMM epilogue's GELU (csrc/gemm_tc.cuh gelu_erf: erfc(z) ~= 2^(-z Q(z)), one MUFU op) evaluated in fp32 with the
+    coefficients parsed from the kernel source stays within 5e-7 of the exact erf GELU (`SA/modeling/common.py:13-26` uses
+    nn.GELU, the erf form) - far below the fp16 rounding of the value it feeds."""
+    import math
+    import os
+    import re
+    src = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "samrs_b200", "csrc", "gemm_tc.cuh")).read()
+    body = src[src.index("__device__ __forceinline__ float gelu_erf(float x)"):]
+    body = body[:body.index("return fmaf(-fabsf(h)")]
+    c = [np.float32(v) for v in re.findall(r"(-?\d\.\d+e[+-]\d+)f", body)]
+    assert len(c) == 6
+    x = np.linspace(-9, 9, 200001).astype(np.float32)
+    z = np.minimum(np.abs(x) * np.float32(0.70710678118654752440), np.float32(4.0)).astype(np.float32)
+    q = (z * c[0] + c[1]).astype(np.float32)
+    for k in c[2:]:
+        q = (q * z + k).astype(np.float32)
+    e = np.exp2((-(z * q)).astype(np.float64)).astype(np.float32)
+    h = (np.float32(0.5) * x).astype(np.float32)
+    got = ((h + np.abs(h)) - np.abs(h) * e).astype(np.float32)
+    want = np.array([0.5 * v * (1.0 + math.erf(v / math.sqrt(2.0))) for v in x.astype(np.float64)])
+    assert np.abs(got - want).max() < 5e-7
