@@ -349,11 +349,24 @@ def predict_torch(w: W, g: SamGeometry, features: Tensor, point_coords: Optional
     return masks, iou, low
 
 
+def apply_image(image_hwc_u8: np.ndarray, target: int = 1024) -> np.ndarray:
+    """`ResizeLongestSide.apply_image` (SA/utils/transforms.py:26-31): torchvision's `resize(to_pil_image(img), size)`
+    is PIL's bilinear resampler on the uint8 image (Pillow = the un-vendored dependency; restated in pil_resize_oracle.py)."""
+    from PIL import Image
+    h, w = image_hwc_u8.shape[:2]
+    scale = target * 1.0 / max(h, w)
+    nh, nw = int(h * scale + 0.5), int(w * scale + 0.5)
+    if (nh, nw) == (h, w):
+        return image_hwc_u8
+    return np.array(Image.fromarray(image_hwc_u8).resize((nw, nh), Image.BILINEAR))
+
+
 def set_image(w: W, g: SamGeometry, image_hwc_u8: np.ndarray, round_gemm_inputs: Optional[str] = None) -> Tensor:
-    """`SamPredictor.set_image` for an image whose long side is already 1024
-    (SA/predictor.py:34-90; `apply_image` is the identity there)."""
-    assert max(image_hwc_u8.shape[:2]) == g.img_size
-    x = torch.as_tensor(image_hwc_u8).permute(2, 0, 1).contiguous()
+    """`SamPredictor.set_image` (SA/predictor.py:34-90): resize the long side to 1024 (identity for 1024x1024 tiles),
+    normalise, zero-pad the short side AFTER normalisation (`Sam.preprocess`, SA/modeling/sam.py:164-174), encode.
+    The size `predict_torch` needs as `input_size` is `apply_image(img).shape[:2]`."""
+    img = apply_image(image_hwc_u8, g.img_size)
+    x = torch.as_tensor(np.ascontiguousarray(img)).permute(2, 0, 1).contiguous()
     return encode_image(w, g, preprocess(x, g.img_size)[None], round_gemm_inputs)
 
 

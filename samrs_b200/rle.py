@@ -37,6 +37,22 @@ def rle_to_mask(rle: Dict[str, Any]) -> np.ndarray:
     return np.repeat(vals, counts).reshape(w, h).T
 
 
+def mask_to_counts(mask: np.ndarray) -> List[int]:
+    """Uncompressed COCO counts of one (h, w) mask that is already on the host (column-major runs, zeros first):
+    what `maskUtils.encode(np.asfortranarray(mask))` run-length encodes (main_sam_hbox_semantic.py:200).  Used by the
+    harness' `pycocotools.mask` stand-in for masks a driver has copied back itself; the device path is `Engine.rle_encode`."""
+    m = np.asarray(mask)
+    if m.ndim != 2:
+        raise ValueError("mask_to_counts expects one (h, w) mask")
+    flat = (m != 0).T.reshape(-1)
+    if flat.size == 0:
+        return []
+    edges = np.flatnonzero(flat[1:] != flat[:-1]) + 1
+    idx = np.concatenate(([0], edges, [flat.size]))
+    runs = np.diff(idx).tolist()
+    return ([0] + runs) if flat[0] else runs
+
+
 def coco_string(counts: Sequence[int]) -> str:
     """Compressed run string: each run (from the third on, its difference to the run two before) in 5-bit groups,
     little-endian, bit 5 = continuation, offset by 48 into printable ASCII.  Parity with pycocotools unpinned."""
@@ -76,13 +92,30 @@ def coco_string_decode(s: str) -> List[int]:
 
 
 def instance_records(counts: torch.Tensor, offsets: torch.Tensor, area: torch.Tensor, h: int, w: int, boxes: np.ndarray,
-                     labels: Sequence[int], categories: Optional[Sequence[str]] = None, compressed: bool = True) -> List[Dict[str, Any]]:
-    """One dict per mask in the drivers' schema; `mask` is a COCO RLE dict (compressed string unless compressed=False)."""
+                     labels: Sequence[int], categories: Optional[Sequence[str]] = None, compressed: bool = True,
+                     rboxes: Optional[np.ndarray] = None) -> List[Dict[str, Any]]:
+    """One dict per mask in the drivers' schema; `mask` is a COCO RLE dict (compressed string unless compressed=False).
+
+    Without `rboxes`: `{mask, bbox, category, label, size}` (main_sam_hbox_semantic.py:204).  With `rboxes` (B,4,2), the
+    rotated-box drivers' variant `{mask, rbox, rhbox, category, label, size}` (main_sam_rhbox_semantic.py:203-209), where
+    `boxes` are the polygons' enclosing horizontal boxes the masks were prompted with (`rhbox`, :120-130)."""
     rles = to_rle_dicts(counts, offsets, h, w)
     sizes = area.detach().cpu().numpy()
     recs = []
     for j, r in enumerate(rles):
         m = {"size": r["size"], "counts": coco_string(r["counts"]) if compressed else r["counts"]}
-        recs.append({"mask": m, "bbox": np.asarray(boxes[j]), "category": categories[int(labels[j])] if categories is not None else None,
-                     "label": int(labels[j]), "size": int(sizes[j])})
+        rec = {"mask": m}
+        if rboxes is None:
+            rec["bbox"] = np.asarray(boxes[j])
+        else:
+            rec["rbox"], rec["rhbox"] = np.asarray(rboxes[j]), np.asarray(boxes[j])
+        rec.update({"category": categories[int(labels[j])] if categories is not None else None, "label": int(labels[j]),
+                    "size": int(sizes[j])})
+        recs.append(rec)
     return recs
+
+
+def enclosing_hboxes(rboxes: np.ndarray) -> np.ndarray:
+    """(B,4,2) polygons -> (B,4) xyxy boxes, the `gt_rhboxes` of main_sam_rhbox_semantic.py:120-130 (dtype follows the input)."""
+    r = np.asarray(rboxes)
+    return np.stack([r[:, :, 0].min(1), r[:, :, 1].min(1), r[:, :, 0].max(1), r[:, :, 1].max(1)], axis=1)

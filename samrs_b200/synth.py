@@ -27,6 +27,21 @@ def labels(idx: int, n: int = 32, classes: int = 18) -> np.ndarray:
     return np.random.default_rng(7_000_003 * (idx + 1)).integers(0, classes, n)
 
 
+def rbox_polys(idx: int, n: int = 32, size: int = 1024) -> np.ndarray:
+    """(n,4,2) float32 rotated-box polygons (vertex order of `obb2poly_np_le90`,
+    Generate Dataset/utils/transform.py:193-216: c-v1-v2, c+v1-v2, c+v1+v2, c-v1+v2), clipped to the tile."""
+    rng = np.random.default_rng(3_000_017 * (idx + 1))
+    c = rng.uniform(128, size - 128, (n, 2))
+    w = rng.uniform(16, 200, n)
+    h = rng.uniform(16, 200, n)
+    th = rng.uniform(-np.pi / 2, np.pi / 2, n)
+    cs, sn = np.cos(th), np.sin(th)
+    v1 = np.stack([w / 2 * cs, w / 2 * sn], 1)
+    v2 = np.stack([-h / 2 * sn, h / 2 * cs], 1)
+    pts = np.stack([c - v1 - v2, c + v1 - v2, c + v1 + v2, c - v1 + v2], axis=1)
+    return np.clip(pts, 0, size - 1).astype(np.float32)
+
+
 def rboxes_5pt(idx: int, n: int = 32, size: int = 1024) -> np.ndarray:
     """(n,5,2) float32 point prompts: 4 rotated-box vertices + centre (BASELINE.json config 3;
     vertex math as `obb2poly_np_le90`, Generate Dataset/utils/transform.py:193-216)."""

@@ -155,10 +155,24 @@ def _draw(key: str, shape: Tuple[int, ...], kind: str, seed: int) -> torch.Tenso
     raise ValueError(kind)
 
 
-def synthetic_state_dict(variant: str, seed: int = 0) -> Dict[str, torch.Tensor]:
-    """Seeded synthetic `Sam.state_dict()` for `variant` (CPU fp32 tensors)."""
+def synthetic_state_dict(variant: str, seed: int = 0, logit_scale: float = 1.0) -> Dict[str, torch.Tensor]:
+    """Seeded synthetic `Sam.state_dict()` for `variant` (CPU fp32 tensors).
+
+    `logit_scale` != 1 multiplies the last layer (weight and bias) of the four hyper-network MLPs, which scales
+    every mask logit by that factor (SURVEY.md H1): default-init weights give |logit| <= 0.4, a trained SAM O(10);
+    parity cases with `logit_scale = 32` state their error relative to that magnitude."""
     g = geometry(variant)
-    return {k: _draw(k, shp, kind, seed) for k, shp, kind in state_dict_spec(g)}
+    sd = {k: _draw(k, shp, kind, seed) for k, shp, kind in state_dict_spec(g)}
+    if logit_scale != 1.0:
+        scale_logits_(sd, logit_scale)
+    return sd
+
+
+def scale_logits_(sd: Dict[str, torch.Tensor], s: float) -> None:
+    """In place: hyper-network output layers x s  =>  low-res mask logits x s (mask_decoder.py:156-167 is linear in them)."""
+    for i in range(4):
+        for nm in ("weight", "bias"):
+            sd[f"mask_decoder.output_hypernetworks_mlps.{i}.layers.2.{nm}"] *= s
 
 
 def check_state_dict(variant, sd: Dict[str, torch.Tensor]) -> None:
