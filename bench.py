@@ -1,25 +1,38 @@
 #!/usr/bin/env python
-"""bench.py -- box-prompted masks/sec, SAM ViT-H, 1024x1024 synthetic RS tiles, 32 hboxes per tile.
+"""bench.py -- box-prompted masks/sec, SAM ViT-H, 1024x1024 synthetic RS tiles (BASELINE.json).
 
-A "step" is one pass of the hot path over one tile: image encoder + prompt encoder + mask decoder for the
-tile's 32 boxes + full-resolution bool masks + the fused semantic label map
-(what one iteration of `Generate Dataset/main_sam_hbox_semantic.py:110-216` computes).
+A "step" is one pass of the hot path over one tile: image encoder + prompt encoder + mask decoder for the tile's
+prompts + full-resolution bool masks + the fused semantic label map (one iteration of
+`Generate Dataset/main_sam_hbox_semantic.py:110-216`).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W]            our engine (one process per GPU under torchrun)
-  python bench.py --impl reference ...                           the reference's CPU path (oracle port) on host cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--config hbox32|pts5|tiny64]     our engine (one process per GPU)
+  python bench.py --impl reference ...                                                   the reference's CPU path
 
-`value`   : whole-job masks/s with tiles and boxes already resident in HBM (CUDA events, max over ranks).
-`e2e`     : same metric through the drop-in `segment_anything.SamPredictor` with HOST buffers: pinned image and
-            boxes copied H2D each step, the driver's 20+12 box chunks, label map copied D2H each step.
-`roofline`: the tcgen05 GEMM (dominant kernel): algorithmic FLOPs per launch / mean launch time, measured with
-            CUDA events on the launching stream inside the timed region (samrs_profile).
+Workloads (`config.workload`):
+  hbox32  32 hboxes per tile, the driver's 20 + 12 chunks end to end          BASELINE.json configs[1]  (default; `metric`)
+  pts5    32 rotated boxes as 5-point prompts (4 vertices + centre)            configs[2]
+  tiny64  64 tiny hboxes per tile (SOTA-density), tile stream                  configs[3]
+The default run also measures pts5 and tiny64 briefly and reports them under `extra_configs`.
+
+`value`     : whole-job masks/s over EXACTLY K timed steps, tiles and prompts already resident in HBM (CUDA events, max over ranks).
+`sustained` : the same step looped for >= 2 s (what the power-capped GPU holds); it runs BEFORE the K timed steps, so `value` is
+              taken in the steady thermal / power state rather than as a 0.2 s burst.
+`e2e`       : same metric through the drop-in `segment_anything.SamPredictor` with HOST buffers: pinned image and prompts copied
+              H2D every step, the driver's chunking, label map copied D2H every step.
+`e2e_full`  : everything one iteration of the driver costs: e2e + on-device COCO-RLE of every mask + D2H of the runs +
+              gray / color PNG + instance pickle written by a thread pool (`samrs_b200.stream.run`).
+`roofline`  : the tcgen05 encoder GEMMs (dominant kernel): algorithmic FLOPs per launch / mean launch time, measured with CUDA events
+              on the launching stream inside a timed pass with one tile in flight (samrs_profile).
+`epilogue`  : the fused HBM-bound epilogue kernels (upsample + threshold + paint): algorithmic bytes / CUDA-event time vs the HBM peak.
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import shutil
 import sys
+import tempfile
 import threading
 import time
 
@@ -35,10 +48,14 @@ from samrs_b200.stream import broadcast_state_dict, max_over_ranks, shard_indice
 from samrs_b200.weights import synthetic_state_dict  # noqa: E402
 
 VARIANT = "vit_h"
-BOXES = 32
 CHUNK = 20                      # the driver's batch_size (main_sam_hbox_semantic.py:91)
 METRIC = "box_prompted_masks_per_sec"
 N_TILES = 4                     # distinct tiles cycled through (weights alone are 1.3 GB >> 126 MB L2)
+WORKLOADS = {
+    "hbox32": {"prompts": 32, "kind": "box", "desc": "SAM ViT-H, 1024x1024 synthetic RS tile, 32 hbox prompts per tile (BASELINE.json configs[1])"},
+    "pts5": {"prompts": 32, "kind": "pts5", "desc": "SAM ViT-H, 1024x1024 synthetic RS tile, 32 rotated boxes as 5-point prompts (BASELINE.json configs[2])"},
+    "tiny64": {"prompts": 64, "kind": "tiny", "desc": "SAM ViT-H, 1024x1024 synthetic RS tile stream, 64 tiny hbox prompts per tile (BASELINE.json configs[3])"},
+}
 
 
 def gemm_flops_per_encode(g) -> float:
@@ -55,8 +72,23 @@ def measured_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), "measured (sustained bf16 cuBLAS, MEASURED_PEAKS.json)"
-    return 1590.0, "fallback (B200_PROFILING.md)"
+        return (float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1590.0))), float(d.get("hbm_gbs", 6650.0)),
+                "measured (MEASURED_PEAKS.json: sustained bf16 cuBLAS, copy bandwidth)")
+    return 1590.0, 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def host_threads() -> int:
+    """Cores this process may really use: the affinity mask capped by the cgroup CPU quota (os.cpu_count() ignores both)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:
+            quota, period = f.read().split()
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    cap = os.environ.get("SAMRS_REF_THREADS")
+    return max(1, min(n, int(cap))) if cap else max(1, n)
 
 
 class ClockSampler:
@@ -114,60 +146,285 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
+def prompts_for(kind: str, idx: int, n: int):
+    """-> (boxes (n,4) or None, point_coords (n,5,2) or None, point_labels or None)."""
+    if kind == "box":
+        return synth.hboxes(idx, n), None, None
+    if kind == "tiny":
+        return synth.hboxes(idx, n, tiny=True), None, None
+    return None, synth.rboxes_5pt(idx, n), np.ones((n, 5), dtype=np.int32)
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
-def cpu_tile(w, g, idx):
-    """One tile through the oracle port exactly as the driver issues it: set_image + 20/12-box predict_torch
-    chunks + the numpy painter."""
-    from oracle import sam_oracle as O
-    img = synth.tile(idx)
-    boxes = torch.from_numpy(synth.hboxes(idx, BOXES))
-    labels = synth.labels(idx, BOXES)
-    with torch.no_grad():
-        feat = O.set_image(w, g, img)
+class ReferenceArm:
+    """The reference's own CPU implementation of one step.  Uses the UNMODIFIED `segment_anything` package staged under
+    oracle/_ref/GD by oracle/stage_ref.py (kind "reference"); if that directory is missing (it is staged at build time in the
+    build container and travels with the snapshot) the oracle port oracle/sam_oracle.py is timed instead (kind "port")."""
+
+    def __init__(self, threads: int):
+        torch.set_num_threads(threads)
+        self.threads = threads
+        self.g = geometry(VARIANT)
+        sd = synthetic_state_dict(VARIANT, 0)
+        gd = os.path.join(ROOT, "oracle", "_ref", "GD")
+        if os.path.isdir(os.path.join(gd, "segment_anything")):
+            sys.path.insert(0, gd)
+            for k in [k for k in sys.modules if k == "segment_anything" or k.startswith("segment_anything.")]:
+                del sys.modules[k]
+            from segment_anything import SamPredictor
+            from segment_anything.build_sam import _build_sam
+            g = self.g
+            sam = _build_sam(g.embed_dim, g.depth, g.num_heads, list(g.global_attn_indexes))
+            sam.load_state_dict(sd, strict=True)
+            self.pred, self.kind = SamPredictor(sam), "reference"
+            self.what = "the reference's segment_anything (oracle/_ref/GD), torch CPU fp32"
+        else:
+            self.w, self.kind = sd, "port"
+            self.what = "oracle/sam_oracle.py (port; oracle/_ref/GD not staged), torch CPU fp32"
+
+    def tile(self, idx: int, wl: dict) -> np.ndarray:
+        """One tile exactly as the driver issues it: set_image + chunked predict_torch + the numpy painter."""
+        n = wl["prompts"]
+        img = synth.tile(idx)
+        boxes, pts, plab = prompts_for(wl["kind"], idx, n)
+        labels = synth.labels(idx, n)
         seg = np.full((1024, 1024), 255, dtype=np.uint8)
-        for s in range(0, BOXES, CHUNK):
-            tb = O.apply_boxes(boxes[s:s + CHUNK], (1024, 1024))
-            masks, _, _ = O.predict_torch(w, g, feat, None, None, tb, None, False)
-            O.painter_reduce(masks[:, 0].numpy(), labels[s:s + CHUNK], seg)
-    return seg
+        with torch.no_grad():
+            if self.kind == "reference":
+                self.pred.set_image(img)
+                for s in range(0, n, CHUNK):
+                    tb = None if boxes is None else self.pred.transform.apply_boxes_torch(torch.from_numpy(boxes[s:s + CHUNK]), img.shape[:2])
+                    pc = None if pts is None else self.pred.transform.apply_coords_torch(torch.from_numpy(pts[s:s + CHUNK]), img.shape[:2])
+                    pl = None if plab is None else torch.from_numpy(plab[s:s + CHUNK])
+                    masks, _, _ = self.pred.predict_torch(point_coords=pc, point_labels=pl, boxes=tb, mask_input=None, multimask_output=False)
+                    m = masks.squeeze(1).cpu().numpy()
+                    for j in range(m.shape[0]):                                   # main_sam_hbox_semantic.py:195-199
+                        r, c = np.nonzero(m[j])
+                        seg[r, c] = labels[s + j]
+            else:
+                from oracle import sam_oracle as O
+                feat = O.set_image(self.w, self.g, img)
+                for s in range(0, n, CHUNK):
+                    tb = None if boxes is None else O.apply_boxes(torch.from_numpy(boxes[s:s + CHUNK]), (1024, 1024))
+                    pc = None if pts is None else torch.from_numpy(pts[s:s + CHUNK])
+                    pl = None if plab is None else torch.from_numpy(plab[s:s + CHUNK])
+                    masks, _, _ = O.predict_torch(self.w, self.g, feat, pc, pl, tb, None, False)
+                    O.painter_reduce(masks[:, 0].numpy(), labels[s:s + CHUNK], seg)
+        return seg
+
+
+def workload_config(name: str, extra: dict) -> dict:
+    c = {"workload": WORKLOADS[name]["desc"], "prompts_per_tile": WORKLOADS[name]["prompts"], "chunk": CHUNK,
+         "weights": "seeded synthetic checkpoint (samrs_b200.weights, seed 0)"}
+    c.update(extra)
+    return c
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    g = geometry(VARIANT)
-    w = synthetic_state_dict(VARIANT, 0)
-    budget = float(os.environ.get("SAMRS_REF_BUDGET_S", "240"))
+    wl = WORKLOADS[args.config]
+    threads = host_threads()
+    arm = ReferenceArm(threads)
+    budget = float(os.environ.get("SAMRS_REF_BUDGET_S", "270"))
     t_start = time.time()
-    warm = min(args.warmup, 1)
+    warm = min(max(args.warmup, 1), 1)
     for i in range(warm):
-        cpu_tile(w, g, 1000 + i)
-    per, done = [], 0
-    for i in range(args.steps):
-        t0 = time.time()
-        cpu_tile(w, g, i)
-        per.append(time.time() - t0)
-        done += 1
-        if time.time() - t_start + per[-1] > budget:
+        arm.tile(1000 + i, wl)
+    t_one = (time.time() - t_start) / max(warm, 1)
+    per = []
+    want = max(3, args.steps)
+    for i in range(want):
+        if len(per) >= 3 and time.time() - t_start + (np.mean(per) if per else t_one) > budget:
             break
+        t0 = time.time()
+        arm.tile(i, wl)
+        per.append(time.time() - t0)
     ms = 1000.0 * float(np.mean(per))
-    val = BOXES / (ms / 1000.0)
+    val = wl["prompts"] / (ms / 1000.0)
     line = {
-        "impl": "reference", "metric": METRIC, "value": val, "unit": "masks/s", "n_gpus": args.gpus, "steps": done,
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "masks/s", "n_gpus": args.gpus, "steps": len(per),
         "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "SAM ViT-H, 1024x1024 synthetic tile, 32 hbox prompts (20+12 chunks), seeded synthetic weights"},
-        "cpu_baseline": {"value": val, "unit": "masks/s", "cores": cores, "kind": "port",
-                         "sample": f"{done} ViT-H tile(s) x 32 boxes through oracle/sam_oracle.py (torch CPU fp32, {cores} threads)"},
+        "config": workload_config(args.config, {"host_threads": threads, "step_spread_s": [round(min(per), 2), round(max(per), 2)]}),
+        "cpu_baseline": {"value": val, "unit": "masks/s", "cores": threads, "kind": arm.kind,
+                         "sample": f"{len(per)} ViT-H tile(s) x {wl['prompts']} prompts through {arm.what}, {threads} threads "
+                                   f"(affinity / cgroup quota; os.cpu_count() = {os.cpu_count()})"},
         "e2e": {"value": val, "unit": "masks/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
+class Rig:
+    """Engines, predictors, streams and the synthetic inputs of one rank."""
+
+    def __init__(self, device, world, rank, NS):
+        import samrs_b200
+        from samrs_b200.engine import Engine
+        self.device, self.world, self.rank, self.NS = device, world, rank, NS
+        self.g = geometry(VARIANT)
+        if world > 1:
+            sd = broadcast_state_dict(self.g, lambda: synthetic_state_dict(VARIANT, 0), device, src=0)
+        else:
+            sd = synthetic_state_dict(VARIANT, 0)
+        # NS tiles in flight per GPU: each has its own engine (activations + weight copy) and CUDA stream, so one tile's
+        # kernel tails / launch gaps are filled by the other tile's kernels (tiles are independent, SURVEY.md 8e)
+        self.engines = []
+        for _ in range(NS):
+            e_ = Engine(VARIANT, device)
+            e_.load_state_dict(sd)
+            self.engines.append(e_)
+        del sd
+        torch.cuda.empty_cache()
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(NS)]
+        sys.path.insert(0, samrs_b200.DROPIN_PATH)
+        from segment_anything import SamPredictor
+        from segment_anything.modeling import Sam
+        self.predictors = []
+        for e_ in self.engines:
+            sam = Sam(self.g)
+            sam.engine, sam._device = e_, e_.device
+            self.predictors.append(SamPredictor(sam))
+        self.canvases = [torch.empty((1024, 1024), dtype=torch.uint8, device=device) for _ in range(NS)]
+        self.idxs = shard_indices(N_TILES * world, rank, world)          # rank r takes tiles r, r+world, ... (files[rank::world])
+        self.tiles_h = [torch.from_numpy(synth.tile(i)).pin_memory() for i in self.idxs]
+        self.tiles_d = [t.to(device) for t in self.tiles_h]
+        self.RING = 4
+        self.outs_h = [torch.empty((1024, 1024), dtype=torch.uint8).pin_memory() for _ in range(self.RING)]
+        self.out_done = [None] * self.RING
+
+    def load_workload(self, name):
+        wl = WORKLOADS[name]
+        n, dev = wl["prompts"], self.device
+        self.wl, self.n = wl, n
+        pr = [prompts_for(wl["kind"], i, n) for i in self.idxs]
+        pin = lambda a: None if a is None else torch.from_numpy(a).pin_memory()
+        self.boxes_h = [pin(p[0]) for p in pr]
+        self.pts_h = [pin(p[1]) for p in pr]
+        self.plab_h = [pin(p[2]) for p in pr]
+        self.labels_h = [torch.from_numpy(synth.labels(i, n)).to(torch.int32).pin_memory() for i in self.idxs]
+        d = lambda t: None if t is None else t.to(dev)
+        self.boxes_d, self.pts_d, self.plab_d = [d(t) for t in self.boxes_h], [d(t) for t in self.pts_h], [d(t) for t in self.plab_h]
+        self.labels_d = [t.to(dev) for t in self.labels_h]
+
+    # one step with everything resident in HBM
+    def step_resident(self, i, ns=None):
+        j, k = i % N_TILES, i % (ns or self.NS)
+        en, canvas = self.engines[k], self.canvases[k]
+        with torch.cuda.stream(self.streams[k]):
+            en.encode(self.tiles_d[j])
+            low, _ = en.decode(boxes=self.boxes_d[j], point_coords=self.pts_d[j], point_labels=self.plab_d[j], multimask_output=False)
+            en.postprocess(low, (1024, 1024), (1024, 1024))
+            canvas.fill_(255)
+            en.semantic_reduce(low, self.labels_d[j], canvas)
+
+    # the same through the drop-in predictor with host buffers; the host consumes label maps with a lag of RING steps
+    def step_e2e(self, i):
+        j, k, r = i % N_TILES, i % self.NS, i % self.RING
+        en, canvas, predictor, dev = self.engines[k], self.canvases[k], self.predictors[k], self.device
+        if self.out_done[r] is not None:
+            self.out_done[r].synchronize()
+        with torch.cuda.stream(self.streams[k]):
+            img = self.tiles_h[j].numpy()                                    # host HWC uint8 (pinned)
+            predictor.set_image(img)                                         # H2D 3 MiB + encoder
+            up = lambda t: None if t is None else t.to(dev, non_blocking=True)
+            bx, pc, pl, lb = up(self.boxes_h[j]), up(self.pts_h[j]), up(self.plab_h[j]), up(self.labels_h[j])
+            canvas.fill_(255)
+            for s in range(0, self.n, CHUNK):                                # the driver's chunks
+                tb = None if bx is None else predictor.transform.apply_boxes_torch(bx[s:s + CHUNK], img.shape[:2])
+                cc = None if pc is None else predictor.transform.apply_coords_torch(pc[s:s + CHUNK], img.shape[:2])
+                _, _, low = predictor.predict_torch(cc, None if pl is None else pl[s:s + CHUNK], boxes=tb, mask_input=None, multimask_output=False)
+                en.semantic_reduce(low, lb[s:s + CHUNK], canvas)
+            self.outs_h[r].copy_(canvas, non_blocking=True)                  # D2H 1 MiB label map
+            ev = torch.cuda.Event()
+            ev.record(self.streams[k])
+            self.out_done[r] = ev
+
+    def h2d_bytes(self):
+        per_prompt = 16 if self.wl["kind"] != "pts5" else 5 * 8 + 5 * 4
+        return 1024 * 1024 * 3 + self.n * per_prompt + self.n * 4
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(self, fn, steps, profile=False, min_seconds=0.0):
+        """Times `steps` calls of fn (or, with min_seconds, as many batches of `steps` as that takes)."""
+        self.barrier()
+        if profile:
+            for e_ in self.engines:
+                e_.profile_begin()
+        l0 = sum(e_.launch_count() for e_ in self.engines)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        cur = torch.cuda.current_stream()
+        a.record(cur)
+        for st_ in self.streams:
+            st_.wait_stream(cur)
+        done, t0 = 0, time.time()
+        while True:
+            for i in range(steps):
+                fn(done + i)
+            done += steps
+            if time.time() - t0 >= min_seconds:
+                break
+            if min_seconds > 0:
+                for st_ in self.streams:                     # keep the host at most one batch ahead of the device
+                    st_.synchronize()
+        for st_ in self.streams:
+            cur.wait_stream(st_)
+        b.record(cur)
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b)
+        prof = None
+        if profile:
+            prof = {}
+            for e_ in self.engines:
+                for k_, (ms_, n_) in e_.profile_end().items():
+                    o = prof.get(k_, (0.0, 0))
+                    prof[k_] = (o[0] + ms_, o[1] + n_)
+        launches = sum(e_.launch_count() for e_ in self.engines) - l0
+        if self.world > 1:
+            ms = max_over_ranks(ms, self.device)
+        self.barrier()
+        return ms, launches, prof, done
+
+
+def e2e_full_pass(rig: Rig, steps: int):
+    """What one iteration of the driver really costs (`main_sam_hbox_semantic.py:110-216`): `stream.run` = set_image + chunked
+    decode + painter + on-device RLE + D2H of label map and runs + gray / color PNG + pickle on a writer pool."""
+    from samrs_b200 import stream
+    from samrs_b200.stream import TileJob
+    mapping = {i: (i * 7 % 256, i * 13 % 256, i * 29 % 256) for i in range(64)}
+    mapping[255] = (255, 255, 255)
+    cats = [f"class{i}" for i in range(64)]
+    out = tempfile.mkdtemp(prefix="samrs_bench_out_")
+    try:
+        def jobs(n):
+            for i in range(n):
+                j = i % N_TILES
+                yield TileJob(f"tile_{rig.rank}_{i:05d}", rig.tiles_h[j].numpy(), rig.boxes_h[j].numpy(), rig.labels_h[j].numpy())
+        with torch.cuda.stream(rig.streams[0]):
+            stream.run(rig.predictors[0], jobs(3), out, mapping, cats, chunk=CHUNK, writer_threads=8, depth=4)   # warm-up
+            rig.barrier()
+            t0 = time.time()
+            stats = stream.run(rig.predictors[0], jobs(steps), out, mapping, cats, chunk=CHUNK, writer_threads=8, depth=4)
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+        files = sum(len(os.listdir(os.path.join(out, d))) for d in ("gray", "color", "ins"))
+    finally:
+        shutil.rmtree(out, ignore_errors=True)
+    if rig.world > 1:
+        dt = max_over_ranks(dt * 1000.0, rig.device) / 1000.0
+    return {"value": rig.world * rig.n * steps / dt, "unit": "masks/s", "ms_per_step": 1000.0 * dt / steps, "steps": steps,
+            "files_written_per_rank": files, "tiles_in_flight_per_gpu": 1,
+            "path": "samrs_b200.stream.run: set_image + chunked decode + semantic_reduce + rle_encode + D2H (label map, runs) + "
+                    "writers.save_tile (gray / color PNG, instance pickle) on 8 writer threads; wall clock incl. file writes"}
+
+
 def run_ours(args):
     import torch.distributed as dist
 
@@ -180,148 +437,30 @@ def run_ours(args):
     device = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
-
-    import samrs_b200
-    from samrs_b200.engine import Engine
-    g = geometry(VARIANT)
-    # NS tiles in flight per GPU: each has its own engine (activations + weight copy) and CUDA stream, so one tile's
-    # kernel tails / launch gaps are filled by the other tile's kernels (tiles are independent)
     NS = max(1, int(os.environ.get("SAMRS_STREAMS", "2")))
-    if world > 1:
-        sd = broadcast_state_dict(g, lambda: synthetic_state_dict(VARIANT, 0), device, src=0)
-    else:
-        sd = synthetic_state_dict(VARIANT, 0)
-    engines = []
-    for _ in range(NS):
-        e_ = Engine(VARIANT, device)
-        e_.load_state_dict(sd)
-        engines.append(e_)
-    eng = engines[0]
-    del sd
-    torch.cuda.empty_cache()
-    streams = [torch.cuda.Stream(device=device) for _ in range(NS)]
+    rig = Rig(device, world, rank, NS)
+    rig.load_workload(args.config)
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        rig.step_resident(i)
+        rig.step_e2e(i)
 
-    # the drop-in predictors share the engines (same weights, no further copies)
-    sys.path.insert(0, samrs_b200.DROPIN_PATH)
-    from segment_anything import SamPredictor
-    from segment_anything.modeling import Sam
-    predictors = []
-    for e_ in engines:
-        sam = Sam(g)
-        sam.engine, sam._device = e_, e_.device
-        predictors.append(SamPredictor(sam))
-
-    # this rank's tiles: rank r takes tiles r, r+world, ... (files[rank::world])
-    idxs = shard_indices(N_TILES * world, rank, world)
-    tiles_h = [torch.from_numpy(synth.tile(i)).pin_memory() for i in idxs]
-    boxes_h = [torch.from_numpy(synth.hboxes(i, BOXES)).pin_memory() for i in idxs]
-    labels_h = [torch.from_numpy(synth.labels(i, BOXES)).to(torch.int32).pin_memory() for i in idxs]
-    tiles_d = [t.to(device) for t in tiles_h]
-    boxes_d = [b.to(device) for b in boxes_h]
-    labels_d = [l.to(device) for l in labels_h]
-    canvases = [torch.empty((1024, 1024), dtype=torch.uint8, device=device) for _ in range(NS)]
-
-    VARIANT_STEP = os.environ.get("SAMRS_BENCH_STEP", "")     # diagnostics only; the reported line uses the default
-
-    def step_resident(i):
-        nonlocal NS
-        j, k = i % N_TILES, i % NS
-        en, canvas = engines[k], canvases[k]
-        with torch.cuda.stream(streams[k]):
-            en.encode(tiles_d[j])
-            if VARIANT_STEP == "chunks":             # diagnostic: the driver's 20 + 12 chunking on resident inputs
-                canvas.fill_(255)
-                for s in range(0, BOXES, CHUNK):
-                    low, _ = en.decode(boxes=boxes_d[j][s:s + CHUNK], multimask_output=False)
-                    en.postprocess(low, (1024, 1024), (1024, 1024))
-                    en.semantic_reduce(low, labels_d[j][s:s + CHUNK], canvas)
-                return
-            low, _ = en.decode(boxes=boxes_d[j], multimask_output=False)
-            en.postprocess(low, (1024, 1024), (1024, 1024))
-            canvas.fill_(255)
-            en.semantic_reduce(low, labels_d[j], canvas)
-
-    # e2e output ring: the host consumes label maps with a lag of RING steps, so the only host wait in a step is for
-    # the D2H of the tile RING steps back (device buffers are reused in stream order and need no host sync)
-    RING = 4
-    outs_h = [torch.empty((1024, 1024), dtype=torch.uint8).pin_memory() for _ in range(RING)]
-    out_done = [None] * RING
-
-    def step_e2e(i):
-        j, k, r = i % N_TILES, i % NS, i % RING
-        en, canvas, predictor = engines[k], canvases[k], predictors[k]
-        if out_done[r] is not None:
-            out_done[r].synchronize()                                    # the host consumed this slot's previous label map
-        with torch.cuda.stream(streams[k]):
-            img = tiles_h[j].numpy()                                    # host HWC uint8 (pinned)
-            predictor.set_image(img)                                     # H2D 3 MiB + encoder
-            bx = boxes_h[j].to(device, non_blocking=True)                # H2D 512 B
-            lb = labels_h[j].to(device, non_blocking=True)
-            canvas.fill_(255)
-            for s in range(0, BOXES, CHUNK):                             # the driver's 20 + 12 chunks
-                tb = predictor.transform.apply_boxes_torch(bx[s:s + CHUNK], img.shape[:2])
-                _, _, low = predictor.predict_torch(None, None, boxes=tb, mask_input=None, multimask_output=False)
-                en.semantic_reduce(low, lb[s:s + CHUNK], canvas)
-            outs_h[r].copy_(canvas, non_blocking=True)                   # D2H 1 MiB label map
-            ev = torch.cuda.Event()
-            ev.record(streams[k])
-            out_done[r] = ev
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def timed(fn, steps, profile=False):
-        barrier()
-        if profile:
-            for e_ in engines:
-                e_.profile_begin()
-        l0 = sum(e_.launch_count() for e_ in engines)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        cur = torch.cuda.current_stream()
-        a.record(cur)
-        for st_ in streams:
-            st_.wait_stream(cur)
-        for i in range(steps):
-            fn(i)
-        for st_ in streams:
-            cur.wait_stream(st_)
-        b.record(cur)
-        torch.cuda.synchronize()
-        ms = a.elapsed_time(b)
-        prof = None
-        if profile:
-            prof = {}
-            for e_ in engines:
-                for k_, (ms_, n_) in e_.profile_end().items():
-                    o = prof.get(k_, (0.0, 0))
-                    prof[k_] = (o[0] + ms_, o[1] + n_)
-        launches = sum(e_.launch_count() for e_ in engines) - l0
-        if world > 1:
-            ms = max_over_ranks(ms, device)
-        barrier()
-        return ms, launches, prof
-
-    for i in range(max(args.warmup, 3)):
-        step_resident(i)
-        step_e2e(i)
     with ClockSampler(local) as clk:
-        ms_res, launches, _ = timed(step_resident, args.steps)
-        ms_e2e, _, _ = timed(step_e2e, args.steps)
+        # sustained window first (>= 2 s): it doubles as a long warm-up, so the K timed steps below see steady clocks
+        ms_sus, _, _, n_sus = rig.timed(rig.step_resident, max(args.steps, 10), min_seconds=float(os.environ.get("SAMRS_SUSTAIN_S", "2.0")))
+        ms_res, launches, _, _ = rig.timed(rig.step_resident, args.steps)
+        ms_e2e, _, _, _ = rig.timed(rig.step_e2e, args.steps)
     clocks = clk.summary()
     # roofline pass: the same step with ONE tile in flight, so that each kernel's CUDA-event duration is its own
-    # (with several tiles in flight kernels of different tiles share the SMs and per-kernel times overlap)
-    ns_saved, NS = NS, 1
     prof_steps = max(2, min(args.steps, 6))
-    ms_single, _, prof = timed(step_resident, prof_steps, profile=True)
-    NS = ns_saved
+    ms_single, _, prof, _ = rig.timed(lambda i: rig.step_resident(i, ns=1), prof_steps, profile=True)
 
-    value = world * BOXES * args.steps / (ms_res / 1000.0)
-    e2e = world * BOXES * args.steps / (ms_e2e / 1000.0)
-    peak, peak_src = measured_peaks()
+    n = rig.n
+    value = world * n * args.steps / (ms_res / 1000.0)
+    e2e = world * n * args.steps / (ms_e2e / 1000.0)
+    peak_tf, peak_gbs, peak_src = measured_peaks()
     gemm_ms, gemm_n = prof["gemm_tc"]
-    flops_per_launch = gemm_flops_per_encode(g) * prof_steps / max(gemm_n, 1)
+    flops_per_launch = gemm_flops_per_encode(rig.g) * prof_steps / max(gemm_n, 1)
     achieved = flops_per_launch / (gemm_ms / max(gemm_n, 1) / 1000.0) / 1e12 if gemm_ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "gemm_traffic.json")
@@ -331,35 +470,62 @@ def run_ours(args):
     step_ms = ms_res / args.steps
     single_ms = ms_single / prof_steps
     shares = {k: round(v[0] / prof_steps, 4) for k, v in prof.items()}
+    # fused epilogue (postprocess + painter): algorithmic bytes = logits in (n x 256 KiB, read by both) + bool masks out + label map
+    epi_ms, epi_n = prof["epilogue"]
+    epi_bytes = prof_steps * (2 * n * 65536 * 4 + n * 1048576 + 2 * 1048576)
+    epi_gbs = epi_bytes / (epi_ms / 1000.0) / 1e9 if epi_ms > 0 else 0.0
 
     line = {
-        "metric": METRIC, "value": value, "unit": "masks/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "metric": METRIC, "value": value, "unit": "masks/s", "n_gpus": world, "steps": args.steps, "warmup": warm,
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f16 tensor-core operands, f32 accumulate / residual / softmax / decoder", "data": "synthetic",
-        "config": {"workload": "SAM ViT-H, 1024x1024 synthetic RS tile, 32 hbox prompts per tile (BASELINE.json configs[1])",
-                   "tiles_per_rank_cycled": N_TILES, "tiles_in_flight_per_gpu": NS, "l2": "working set (1.3 GB fp16 weights) exceeds the 126 MB L2",
-                   "parallelism": f"tile-sharded dp{world}, weights broadcast once over NCCL" if world > 1 else "single GPU",
-                   "step": "encode + decode(32) + bool masks + fused label map"},
+        "config": workload_config(args.config, {
+            "tiles_per_rank_cycled": N_TILES, "tiles_in_flight_per_gpu": NS, "l2": "working set (1.3 GB fp16 weights) exceeds the 126 MB L2",
+            "parallelism": f"tile-sharded dp{world}, weights broadcast once over NCCL" if world > 1 else "single GPU",
+            "step": "encode + decode(all prompts) + bool masks + fused label map"}),
         "gpu_launches": launches,
-        "e2e": {"value": e2e, "unit": "masks/s", "h2d_bytes_per_step": 1024 * 1024 * 3 + BOXES * 16 + BOXES * 4,
-                "d2h_bytes_per_step": 1024 * 1024, "ms_per_step": ms_e2e / args.steps,
-                "path": "segment_anything.SamPredictor.set_image + predict_torch (20+12 chunks) + semantic_reduce"},
-        "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 cta_group::2 / ::1, fp16 in, fp32 acc): every encoder GEMM launch", "achieved": achieved, "peak": peak,
-                     "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": traffic,
+        "sustained": {"value": world * n * n_sus / (ms_sus / 1000.0), "unit": "masks/s", "seconds": ms_sus / 1000.0, "steps": n_sus,
+                      "note": "same resident step looped >= 2 s, run before the K timed steps"},
+        "e2e": {"value": e2e, "unit": "masks/s", "h2d_bytes_per_step": rig.h2d_bytes(), "d2h_bytes_per_step": 1024 * 1024,
+                "ms_per_step": ms_e2e / args.steps,
+                "path": "segment_anything.SamPredictor.set_image + predict_torch (chunks of 20) + semantic_reduce, pinned host buffers"},
+        "roofline": {"bound": "tensor", "kernel": "gemm_tc2_kernel / gemm_tc_kernel (tcgen05 cta_group::2 / ::1, fp16 in, fp32 acc): every encoder GEMM launch",
+                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf, "peak_source": peak_src, "traffic": traffic,
                      "launches_per_step": gemm_n / prof_steps, "share_of_step": (gemm_ms / prof_steps) / single_ms,
                      "measured": "CUDA events around every launch on its stream, one tile in flight"},
+        "epilogue": {"bound": "hbm", "kernel": "upsample4_threshold_kernel + upsample4_paint_kernel", "achieved": epi_gbs, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": epi_gbs / peak_gbs, "ms_per_step": epi_ms / prof_steps, "bytes_per_step": epi_bytes / prof_steps},
         "single_tile_in_flight": {"ms_per_step": single_ms, "ms_per_step_by_kernel": shares},
         "clocks": clocks,
     }
+    if not args.no_extra:
+        k2 = max(4, args.steps // 2)
+        try:
+            line["e2e_full"] = e2e_full_pass(rig, max(args.steps, 12))
+        except Exception as ex:                                   # the headline must not die with an auxiliary measurement
+            line["e2e_full"] = {"error": repr(ex)[:300]}
+        if args.config == "hbox32":
+            extra = {}
+            for name in ("pts5", "tiny64"):
+                rig.load_workload(name)
+                for i in range(3):
+                    rig.step_resident(i)
+                    rig.step_e2e(i)
+                mr, _, _, _ = rig.timed(rig.step_resident, k2)
+                me, _, _, _ = rig.timed(rig.step_e2e, k2)
+                extra[name] = {"workload": WORKLOADS[name]["desc"], "steps": k2, "value": world * rig.n * k2 / (mr / 1000.0),
+                               "ms_per_step": mr / k2, "e2e": world * rig.n * k2 / (me / 1000.0), "e2e_ms_per_step": me / k2,
+                               "unit": "masks/s", "h2d_bytes_per_step": rig.h2d_bytes(), "d2h_bytes_per_step": 1024 * 1024}
+            line["extra_configs"] = extra
+            rig.load_workload(args.config)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        w = synthetic_state_dict(VARIANT, 0)
+        threads = host_threads()
+        arm = ReferenceArm(threads)
         t0 = time.time()
-        cpu_tile(w, g, 0)
+        arm.tile(0, WORKLOADS[args.config])
         dt = time.time() - t0
-        line["cpu_baseline"] = {"value": BOXES / dt, "unit": "masks/s", "cores": cores, "kind": "port",
-                                "sample": f"1 ViT-H tile x 32 boxes through oracle/sam_oracle.py (torch CPU fp32, {cores} threads, {dt:.1f} s)"}
+        line["cpu_baseline"] = {"value": n / dt, "unit": "masks/s", "cores": threads, "kind": arm.kind,
+                                "sample": f"1 ViT-H tile x {n} prompts through {arm.what}, {threads} threads, {dt:.1f} s (first call, includes thread-pool warm-up)"}
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -372,7 +538,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="hbox32", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip e2e_full and the pts5 / tiny64 side measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

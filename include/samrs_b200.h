@@ -60,6 +60,11 @@ int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int i
 int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_ids, int B,
                           uint8_t* label_map_inout, int H, int W, void* stream);
 
+/* the same painter reduce over bool masks of any size (tiles whose original size is not 1024 x 1024: the masks come from
+ * samrs_postprocess): main_sam_hbox_semantic.py:195-199; highest box index wins, composes across chunks. */
+int samrs_paint_masks(void* engine, const uint8_t* masks /*[B][H][W]*/, const int* class_ids, int B, int H, int W,
+                      uint8_t* label_map_inout, void* stream);
+
 /* image resize of the predictor on the device: replaces ResizeLongestSide.apply_image
  * -- segment_anything/utils/transforms.py:26-31 (torchvision resize of a PIL image == PIL.Image.resize(BILINEAR)).
  * src (H,W,3) uint8 -> dst (out_h,out_w,3) uint8, both on the device, bit-identical to Pillow's two-pass 8-bit

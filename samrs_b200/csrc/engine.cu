@@ -5,6 +5,7 @@
 
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../../include/samrs_b200.h"
@@ -94,35 +95,58 @@ int make_tmap_out(CUtensorMap* out, const void* base, bool half, uint64_t N, uin
   return 0;
 }
 
-// ------------------------------------------------------------------ GEMM launcher
-static int64_t* g_launch_counter = nullptr;   // points into the active engine
+// ------------------------------------------------------------------ per-engine launch state
+// Everything a launch helper needs from "the engine this ABI call serves" lives in the engine's LaunchCtx; the ABI entry
+// points publish it for the duration of the call through a thread_local pointer (LaunchScope), so two host threads can
+// drive two engines concurrently and an engine on another device opts its kernels into large shared memory itself.
+enum ProfCat { PC_GEMM = 0, PC_ATTN_WIN, PC_ATTN_GLOB, PC_RELPOS, PC_LN, PC_ENC_OTHER, PC_DECODER, PC_EPILOGUE, PC_COUNT };
+struct ProfRec { int cat; cudaEvent_t a, b; };
+struct Profiler {
+  bool on = false;
+  std::vector<ProfRec> recs;
+  std::vector<cudaEvent_t> pool;
+  cudaEvent_t get() {
+    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+  }
+};
+struct LaunchCtx {
+  int64_t launches = 0;
+  Profiler prof;
+  float* splitk_ws = nullptr;                     // split-K partial sums of the token-side SGEMMs
+  size_t splitk_ws_floats = 0;
+  std::unordered_set<const void*> smem_opted;     // kernels whose dynamic-smem limit was raised on this engine's device
+  bool capturing = false;                         // a CUDA graph is being captured: no events, no attribute calls
+};
+static thread_local LaunchCtx* t_ctx = nullptr;
 static inline void count_launch(int n = 1) {
-  if (g_launch_counter) *g_launch_counter += n;
+  if (t_ctx) t_ctx->launches += n;
+}
+template <typename K>
+static int opt_in_smem(K kernel, int bytes) {
+  const void* key = reinterpret_cast<const void*>(kernel);
+  if (t_ctx && t_ctx->smem_opted.count(key)) return 0;
+  SAMRS_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  if (t_ctx) t_ctx->smem_opted.insert(key);
+  return 0;
 }
 
 template <int BN, bool OH, int ACT>
 static int launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAMRS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OH, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  SAMRS_TRY(opt_in_smem(gemm_tc_kernel<BN, OH, ACT>, Cfg::kSmemBytes));
   gemm_tc_kernel<BN, OH, ACT><<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(tA, tB, tC, p);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
 }
 
+#ifdef SAMRS_EXPERIMENTS
 // cluster-multicast variant (CM = 2): launched with a (2,1,1) cluster
 template <int BN, bool OH, int ACT>
 static int launch_gemm_mc_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAMRS_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<BN, OH, ACT, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  SAMRS_TRY(opt_in_smem(gemm_tc_kernel<BN, OH, ACT, 2>, Cfg::kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(GEMM_THREADS);
@@ -137,15 +161,12 @@ static int launch_gemm_mc_inst(const CUtensorMap& tA, const CUtensorMap& tB, con
   count_launch();
   return 0;
 }
+#endif
 
 template <int BN, bool OH, int ACT>
 static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAMRS_CUDA_OK(cudaFuncSetAttribute(gemm_tc2_kernel<BN, OH, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
-    attr_done = true;
-  }
+  SAMRS_TRY(opt_in_smem(gemm_tc2_kernel<BN, OH, ACT>, Cfg::kSmemBytes));
   gemm_tc2_kernel<BN, OH, ACT><<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(tA, tB, tC, p);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
@@ -176,6 +197,7 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
     // (it halves the B bytes each SM pulls from L2; 1-CTA tiles are feed-bound once the issue loop is tight)
     bn = (p.N == 1280) ? 160 : 224;
     pair = true;
+#ifdef SAMRS_EXPERIMENTS
     // experiment hook: SAMRS_BN="n1280,n3840,n5120" with force_bn codes (e.g. "160,224,256" = 1-CTA kernels)
     static int env_bn[3] = {-1, 0, 0};
     if (env_bn[0] < 0) {
@@ -186,13 +208,13 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
     if (ov > 0) { bn = ov % 1000; pair = ov >= 1000 && ov < 2000; }
     static const bool use_mcast = getenv("SAMRS_GEMM_MCAST") != nullptr;
     mcast = use_mcast;
+#endif
   } else if (force_bn == 0) {
     // pick the (kernel, N tile) with the smallest modelled duration = waves x per-tile time
     const int cands[4] = {256, 224, 160, 128};
     double best = 1e30;
     for (int pr = 0; pr < 2; ++pr) {
-      static const bool no_pair = getenv("SAMRS_NO_PAIR") != nullptr;
-      if (pr == 1 && (no_pair || p.batch != 1 || a_map_rank3 || p.M < 256 || (num_sms & 1))) continue;
+      if (pr == 1 && (p.batch != 1 || a_map_rank3 || p.M < 256 || (num_sms & 1))) continue;
       for (int i = 0; i < 4; ++i) {
         const int c = cands[i];
         const long tm = (p.M + (pr ? 255 : 127)) / (pr ? 256 : 128), tn = (p.N + c - 1) / c;
@@ -231,6 +253,7 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
 #undef SAMRS_GEMM2_CASE
     SAMRS_FAIL("gemm: unsupported N tile");
   }
+#ifdef SAMRS_EXPERIMENTS
   if (mcast) {
     const int gridm = (tiles < num_sms ? tiles : num_sms) & ~1;
 #define SAMRS_GEMMMC_CASE(BN_)                                                                        \
@@ -246,6 +269,9 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
 #undef SAMRS_GEMMMC_CASE
     SAMRS_FAIL("gemm: unsupported N tile for the multicast kernel");
   }
+#else
+  if (mcast) SAMRS_FAIL("gemm: the TMA-multicast variant exists only in -DSAMRS_EXPERIMENTS builds");
+#endif
   const int grid = tiles < num_sms ? tiles : num_sms;
 #define SAMRS_GEMM_CASE(BN_)                                                                        \
   if (bn == BN_) {                                                                                  \
@@ -263,24 +289,12 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
 }
 
 // ------------------------------------------------------------------ per-category device timing (bench.py roofline)
-enum ProfCat { PC_GEMM = 0, PC_ATTN_WIN, PC_ATTN_GLOB, PC_RELPOS, PC_LN, PC_ENC_OTHER, PC_DECODER, PC_EPILOGUE, PC_COUNT };
-struct ProfRec { int cat; cudaEvent_t a, b; };
-struct Profiler {
-  bool on = false;
-  std::vector<ProfRec> recs;
-  std::vector<cudaEvent_t> pool;
-  cudaEvent_t get() {
-    if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
-    cudaEvent_t e; cudaEventCreate(&e); return e;
-  }
-};
-static Profiler* g_prof = nullptr;
 struct ProfScope {
   cudaStream_t st; ProfRec r; bool active;
-  ProfScope(int cat, cudaStream_t s) : st(s), active(g_prof && g_prof->on) {
-    if (active) { r.cat = cat; r.a = g_prof->get(); r.b = g_prof->get(); cudaEventRecord(r.a, st); }
+  ProfScope(int cat, cudaStream_t s) : st(s), active(t_ctx && t_ctx->prof.on && !t_ctx->capturing) {
+    if (active) { r.cat = cat; r.a = t_ctx->prof.get(); r.b = t_ctx->prof.get(); cudaEventRecord(r.a, st); }
   }
-  ~ProfScope() { if (active) { cudaEventRecord(r.b, st); g_prof->recs.push_back(r); } }
+  ~ProfScope() { if (active) { cudaEventRecord(r.b, st); t_ctx->prof.recs.push_back(r); } }
 };
 
 // ------------------------------------------------------------------ engine state
@@ -308,10 +322,11 @@ struct Engine {
   int D = 0, depth = 0, heads = 0, hd = 0;
   std::vector<int> global_idx;
   int num_sms = 148;
-  int64_t launches = 0;
-  Profiler prof;
+  LaunchCtx ctx;
   std::string err;
-  std::vector<void*> allocs;
+  std::vector<void*> allocs;             // activations and scratch: live until samrs_destroy or release()
+  std::vector<void*> weight_allocs;      // everything load_weights_impl allocates: freed when weights are loaded again
+  bool loading_weights = false;
   bool weights_loaded = false, image_set = false;
 
   // encoder weights
@@ -340,8 +355,9 @@ struct Engine {
   // per-image decoder cache
   float *src0, *K0, *V0, *Qi0;
   float* pp_full = nullptr;            // postprocess scratch for non-1024 sizes
-  struct ResizeTab { int in, out, ksize; int* bounds; int* kk; };
-  std::vector<ResizeTab> resize_tabs;   // Pillow tap tables per (input size, output size), built on first use
+  struct ResizeTab { int in, out, ksize; int* bounds; int* kk; std::vector<int> h_bounds, h_kk; unsigned long long used; };
+  std::vector<ResizeTab> resize_tabs;   // Pillow tap tables per (input size, output size), built on first use; LRU of 32
+  unsigned long long resize_clock = 0;
   uint8_t* resize_tmp = nullptr;       // horizontal-pass result [H][out_w][3]
   size_t resize_tmp_bytes = 0;
   uint32_t* rle_packed = nullptr;      // run-length encoder scratch: column-major bit planes [B][ceil(H/32)][W]
@@ -349,14 +365,13 @@ struct Engine {
   long long* rle_runs = nullptr;       // [rle_runs_cap] runs per mask
   long long* rle_tstate = nullptr;     // [rle_runs_cap][1024][2] per-thread (transitions, last position) of the count pass
   int rle_runs_cap = 0;
-  float* splitk_ws = nullptr;          // split-K partial sums of the token-side SGEMMs
-  size_t splitk_ws_floats = 0;
   float* d_t2i_part = nullptr;         // [cap][8][16][8][18] key-chunk partials of the token->image attention
   // decoder scratch (sized for dec_cap prompts)
   int dec_cap = 0;
-  float *d_tok0, *d_q, *d_tmp256a, *d_tmp256b, *d_tmp256c, *d_tmp256d, *d_tmp128a, *d_tmp128b, *d_tmp128c, *d_mlp;
-  float *d_keys, *d_P, *d_hyper, *d_hy_t, *d_hy_a, *d_hy_b, *d_iou_all, *d_low;
-  __half *d_keysA, *d_ioA;
+  float *d_tok0 = nullptr, *d_q = nullptr, *d_tmp256a = nullptr, *d_tmp256b = nullptr, *d_tmp256c = nullptr, *d_tmp256d = nullptr;
+  float *d_tmp128a = nullptr, *d_tmp128b = nullptr, *d_tmp128c = nullptr, *d_mlp = nullptr;
+  float *d_keys = nullptr, *d_P = nullptr, *d_hyper = nullptr, *d_hy_t = nullptr, *d_hy_a = nullptr, *d_hy_b = nullptr, *d_iou_all = nullptr, *d_low = nullptr;
+  __half *d_keysA = nullptr, *d_ioA = nullptr;
   int mask_cap = 0;                    // mask-prompt path scratch (per-prompt layer-0 operands), allocated on first use
   float *d_Kp = nullptr, *d_Vp = nullptr, *d_Qp = nullptr, *d_src = nullptr;
 
@@ -364,9 +379,25 @@ struct Engine {
   int alloc(T** p, size_t n) {
     void* q = nullptr;
     if (cudaMalloc(&q, n * sizeof(T) + 256) != cudaSuccess) return samrs::fail(__FILE__, __LINE__, "cudaMalloc failed");
-    allocs.push_back(q);
+    (loading_weights ? weight_allocs : allocs).push_back(q);
     *p = reinterpret_cast<T*>(q);
     return 0;
+  }
+  // give a superseded scratch buffer back (cudaFree waits for the device: only reached when a buffer has to grow)
+  template <typename T>
+  void release(T** p) {
+    if (*p == nullptr) return;
+    void* q = reinterpret_cast<void*>(*p);
+    for (size_t i = 0; i < allocs.size(); ++i)
+      if (allocs[i] == q) { allocs[i] = allocs.back(); allocs.pop_back(); cudaFree(q); break; }
+    *p = nullptr;
+  }
+  void free_weights() {
+    if (weight_allocs.empty()) return;
+    cudaDeviceSynchronize();
+    for (void* q : weight_allocs) cudaFree(q);
+    weight_allocs.clear();
+    weights_loaded = image_set = false;
   }
 };
 
@@ -377,8 +408,6 @@ static int set_err(Engine* e, int rc) {
 
 static void* g_attn_dbg = nullptr;            // device buffer for attention pipeline traces (tools only)
 // ------------------------------------------------------------------ small launch helpers
-static float* g_splitk_ws = nullptr;          // split-K workspace of the active engine (set by LaunchScope)
-static size_t g_splitk_ws_floats = 0;
 static int sgemm(cudaStream_t st, const float* A, int lda, const float* W, int ldw, float* C, int ldc, const float* bias,
                  const float* R, int ldr, int rmod, int M, int N, int K, int act) {
   if (K % 16 != 0 || lda % 4 != 0 || ldw % 4 != 0) SAMRS_FAIL("sgemm: K must be a multiple of 16");
@@ -386,14 +415,15 @@ static int sgemm(cudaStream_t st, const float* A, int lda, const float* W, int l
   if (M <= 2048 && K % 64 == 0) {
     // token-side GEMM: latency-bound, 64-deep k slices; split K >= 1024 across blockIdx.z (deterministic reduce)
     int splits = 1;
-    if (K >= 1024 && g_splitk_ws && size_t(M) * N * 8 <= g_splitk_ws_floats) splits = 8;
+    float* ws = t_ctx ? t_ctx->splitk_ws : nullptr;
+    if (K >= 1024 && ws && size_t(M) * N * 8 <= t_ctx->splitk_ws_floats) splits = 8;
     const int kps = ((K / splits + 63) / 64) * 64;
     dim3 grid((M + 63) / 64, (N + 63) / 64, splits);
-    sgemm_small_kernel<<<grid, 256, 0, st>>>(p, kps, splits > 1 ? g_splitk_ws : nullptr);
+    sgemm_small_kernel<<<grid, 256, 0, st>>>(p, kps, splits > 1 ? ws : nullptr);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
     if (splits > 1) {
-      splitk_reduce_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(p, g_splitk_ws, splits);
+      splitk_reduce_kernel<<<(M * N + 255) / 256, 256, 0, st>>>(p, ws, splits);
       SAMRS_CUDA_OK(cudaGetLastError());
       count_launch();
     }
@@ -414,8 +444,7 @@ static int ln_rows(cudaStream_t st, const float* in, int ld_in, const float* g, 
   const int grid = (rows + rows_per_block - 1) / rows_per_block;
   if (C % 4 != 0) SAMRS_FAIL("layernorm: C must be a multiple of 4");
   if constexpr (sizeof(OutT) == 2 && ACT == 0) {
-    static const bool no_stream = getenv("SAMRS_LN_ROWS") != nullptr;   // experiment hook: the one-row-per-warp kernel
-    if (!no_stream && rows >= 1024 && (C == 1280 || C == 1024 || C == 768)) {
+    if (rows >= 1024 && (C == 1280 || C == 1024 || C == 768)) {
       const int g4 = (rows + 3) / 4;
       if (C == 1280) ln_rows_stream_kernel<10><<<g4, 64, 0, st>>>(in, ld_in, g, b, eps, reinterpret_cast<__half*>(out), ld_out, rows);
       else if (C == 1024) ln_rows_stream_kernel<8><<<g4, 64, 0, st>>>(in, ld_in, g, b, eps, reinterpret_cast<__half*>(out), ld_out, rows);
@@ -436,29 +465,9 @@ static int ln_rows(cudaStream_t st, const float* in, int ld_in, const float* g, 
 }
 
 template <int HD, int BX, int QBY, int KBY, int NKT>
-static int launch_attn_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, const AttnParams& p, int num_sms, cudaStream_t st) {
-  using C = AttnCfg<HD, BX, QBY, KBY, NKT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAMRS_CUDA_OK(cudaFuncSetAttribute(attn_tc_kernel<HD, BX, QBY, KBY, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_done = true;
-  }
-  const int items = p.num_qtiles * p.heads;
-  const int grid = items < num_sms ? items : num_sms;
-  attn_tc_kernel<HD, BX, QBY, KBY, NKT><<<grid, 256, C::kSmemBytes, st>>>(tQ, tKV, p);
-  SAMRS_CUDA_OK(cudaGetLastError());
-  count_launch();
-  return 0;
-}
-
-template <int HD, int BX, int QBY, int KBY, int NKT>
 static int launch_attn2_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, const AttnParams& p, int num_sms, cudaStream_t st) {
   using C = Attn2Cfg<HD, BX, QBY, KBY, NKT>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAMRS_CUDA_OK(cudaFuncSetAttribute(attn_tc2_kernel<HD, BX, QBY, KBY, NKT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
-    attr_done = true;
-  }
+  SAMRS_TRY(opt_in_smem(attn_tc2_kernel<HD, BX, QBY, KBY, NKT>, C::kSmemBytes));
   const int units = p.num_qtiles * p.heads;
   const int grid = units < num_sms ? units : num_sms;
   attn_tc2_kernel<HD, BX, QBY, KBY, NKT><<<grid, 384, C::kSmemBytes, st>>>(tQ, tKV, p);
@@ -483,9 +492,8 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
     gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f; gp.dbg = nullptr; gp.dbg_mode = 0; gp.accumulate = 0;
     // attention v2: the epilogue writes fp16(G / scale_log2e), the value the attention kernel feeds to its bias MMA, which
     // halves the bytes written here and gathered there (global blocks: 67 -> 34 MB per layer)
-    static const bool v1 = getenv("SAMRS_ATTN_V1") != nullptr;
-    const bool g16 = !v1;
-    if (g16) gp.out_scale = 1.0f / ((1.0f / sqrtf(float(hd))) * 1.4426950408889634f);
+    const bool g16 = true;
+    gp.out_scale = 1.0f / ((1.0f / sqrtf(float(hd))) * 1.4426950408889634f);
     SAMRS_TRY(launch_gemm_tc(nullptr, 8, reltab, hd, gp, g16, 0, e->num_sms, st, global ? 256 : 128, &tA));
   }
   ProfScope ps2(global ? PC_ATTN_GLOB : PC_ATTN_WIN, st);
@@ -497,33 +505,21 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
   p.heads = e->heads;
   p.scale_log2e = (1.0f / sqrtf(float(hd))) * 1.4426950408889634f;
   p.dbg = static_cast<unsigned long long*>(g_attn_dbg);
-  static const bool pv_split = getenv("SAMRS_ATTN_PV_SPLIT") != nullptr;
-  p.pv_split = pv_split ? 1 : 0;
+  p.pv_split = 0;
   CUtensorMap tQ, tKV;
   const uint64_t pitch_x = uint64_t(3 * D) * 2, pitch_y = pitch_x * 64;
-  static const bool attn_v1 = getenv("SAMRS_ATTN_V1") != nullptr;     // first-generation kernel (one query tile per CTA)
   if (global) {
-    p.num_qtiles = 32;
+    p.num_qtiles = 16;                                                // pairs of 128-query tiles
     SAMRS_TRY(make_tmap_3d(&tQ, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 64, 2));
     tKV = tQ;
-    if (!attn_v1) {
-      p.num_qtiles = 16;                                              // pairs of 128-query tiles
-      if (hd == 64) return launch_attn2_inst<64, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
-      return launch_attn2_inst<80, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
-    }
-    if (hd == 64) return launch_attn_inst<64, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
-    return launch_attn_inst<80, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
+    if (hd == 64) return launch_attn2_inst<64, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
+    return launch_attn2_inst<80, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
   }
-  p.num_qtiles = 50;
+  p.num_qtiles = 25;                                                  // windows (two 7-row halves each)
   SAMRS_TRY(make_tmap_3d(&tQ, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 14, 7));
   SAMRS_TRY(make_tmap_3d(&tKV, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 14, 14));
-  if (!attn_v1) {
-    p.num_qtiles = 25;                                                // windows (two 7-row halves each)
-    if (hd == 64) return launch_attn2_inst<64, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
-    return launch_attn2_inst<80, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
-  }
-  if (hd == 64) return launch_attn_inst<64, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
-  return launch_attn_inst<80, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
+  if (hd == 64) return launch_attn2_inst<64, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
+  return launch_attn2_inst<80, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
 }
 
 // ------------------------------------------------------------------ weight ingest
@@ -792,38 +788,38 @@ static int alloc_activations(Engine* e) {
   SAMRS_TRY(e->alloc(&e->K0, T * 128));
   SAMRS_TRY(e->alloc(&e->V0, T * 128));
   SAMRS_TRY(e->alloc(&e->Qi0, T * 128));
-  e->splitk_ws_floats = size_t(8) * 1024 * 2048;
-  SAMRS_TRY(e->alloc(&e->splitk_ws, e->splitk_ws_floats));
+  e->ctx.splitk_ws_floats = size_t(8) * 1024 * 2048;
+  SAMRS_TRY(e->alloc(&e->ctx.splitk_ws, e->ctx.splitk_ws_floats));
   return 0;
 }
 
 static int ensure_decoder_scratch(Engine* e, int B) {
   if (B <= e->dec_cap) return 0;
-  // scratch is never freed individually; grow geometrically (old buffers are released with the engine)
+  // grow geometrically; the superseded buffers are given back first (cudaFree waits for work that still uses them)
   int cap = e->dec_cap ? e->dec_cap : 32;
   while (cap < B) cap *= 2;
   const size_t c = cap, TT = 16;
-  SAMRS_TRY(e->alloc(&e->d_tok0, c * TT * 256));
-  SAMRS_TRY(e->alloc(&e->d_q, c * TT * 256));
-  SAMRS_TRY(e->alloc(&e->d_tmp256a, c * TT * 256));
-  SAMRS_TRY(e->alloc(&e->d_tmp256b, c * TT * 256));
-  SAMRS_TRY(e->alloc(&e->d_tmp256c, c * TT * 256));
-  SAMRS_TRY(e->alloc(&e->d_tmp256d, c * TT * 256));
-  SAMRS_TRY(e->alloc(&e->d_tmp128a, c * TT * 128));
-  SAMRS_TRY(e->alloc(&e->d_tmp128b, c * TT * 128));
-  SAMRS_TRY(e->alloc(&e->d_tmp128c, c * TT * 128));
-  SAMRS_TRY(e->alloc(&e->d_mlp, c * TT * 2048));
-  SAMRS_TRY(e->alloc(&e->d_t2i_part, c * 8 * 16 * 8 * 18));
-  SAMRS_TRY(e->alloc(&e->d_keys, c * 4096 * 256));
-  SAMRS_TRY(e->alloc(&e->d_P, c * 4096 * 512));
-  SAMRS_TRY(e->alloc(&e->d_keysA, c * 4096 * 768));
-  SAMRS_TRY(e->alloc(&e->d_ioA, c * 4096 * 384));
-  SAMRS_TRY(e->alloc(&e->d_hyper, c * 4 * 32));
-  SAMRS_TRY(e->alloc(&e->d_hy_t, c * 256));
-  SAMRS_TRY(e->alloc(&e->d_hy_a, c * 256));
-  SAMRS_TRY(e->alloc(&e->d_hy_b, c * 256));
-  SAMRS_TRY(e->alloc(&e->d_iou_all, c * 4));
-  SAMRS_TRY(e->alloc(&e->d_low, c * 3 * 65536));
+  e->release(&e->d_tok0); SAMRS_TRY(e->alloc(&e->d_tok0, c * TT * 256));
+  e->release(&e->d_q); SAMRS_TRY(e->alloc(&e->d_q, c * TT * 256));
+  e->release(&e->d_tmp256a); SAMRS_TRY(e->alloc(&e->d_tmp256a, c * TT * 256));
+  e->release(&e->d_tmp256b); SAMRS_TRY(e->alloc(&e->d_tmp256b, c * TT * 256));
+  e->release(&e->d_tmp256c); SAMRS_TRY(e->alloc(&e->d_tmp256c, c * TT * 256));
+  e->release(&e->d_tmp256d); SAMRS_TRY(e->alloc(&e->d_tmp256d, c * TT * 256));
+  e->release(&e->d_tmp128a); SAMRS_TRY(e->alloc(&e->d_tmp128a, c * TT * 128));
+  e->release(&e->d_tmp128b); SAMRS_TRY(e->alloc(&e->d_tmp128b, c * TT * 128));
+  e->release(&e->d_tmp128c); SAMRS_TRY(e->alloc(&e->d_tmp128c, c * TT * 128));
+  e->release(&e->d_mlp); SAMRS_TRY(e->alloc(&e->d_mlp, c * TT * 2048));
+  e->release(&e->d_t2i_part); SAMRS_TRY(e->alloc(&e->d_t2i_part, c * 8 * 16 * 8 * 18));
+  e->release(&e->d_keys); SAMRS_TRY(e->alloc(&e->d_keys, c * 4096 * 256));
+  e->release(&e->d_P); SAMRS_TRY(e->alloc(&e->d_P, c * 4096 * 512));
+  e->release(&e->d_keysA); SAMRS_TRY(e->alloc(&e->d_keysA, c * 4096 * 768));
+  e->release(&e->d_ioA); SAMRS_TRY(e->alloc(&e->d_ioA, c * 4096 * 384));
+  e->release(&e->d_hyper); SAMRS_TRY(e->alloc(&e->d_hyper, c * 4 * 32));
+  e->release(&e->d_hy_t); SAMRS_TRY(e->alloc(&e->d_hy_t, c * 256));
+  e->release(&e->d_hy_a); SAMRS_TRY(e->alloc(&e->d_hy_a, c * 256));
+  e->release(&e->d_hy_b); SAMRS_TRY(e->alloc(&e->d_hy_b, c * 256));
+  e->release(&e->d_iou_all); SAMRS_TRY(e->alloc(&e->d_iou_all, c * 4));
+  e->release(&e->d_low); SAMRS_TRY(e->alloc(&e->d_low, c * 3 * 65536));
   e->dec_cap = cap;
   return 0;
 }
@@ -833,10 +829,10 @@ static int ensure_mask_scratch(Engine* e, int B) {
   int cap = e->mask_cap ? e->mask_cap : 8;
   while (cap < B) cap *= 2;
   const size_t c = cap;
-  SAMRS_TRY(e->alloc(&e->d_Kp, c * 4096 * 128));
-  SAMRS_TRY(e->alloc(&e->d_Vp, c * 4096 * 128));
-  SAMRS_TRY(e->alloc(&e->d_Qp, c * 4096 * 128));
-  SAMRS_TRY(e->alloc(&e->d_src, c * 4096 * 256));
+  e->release(&e->d_Kp); SAMRS_TRY(e->alloc(&e->d_Kp, c * 4096 * 128));
+  e->release(&e->d_Vp); SAMRS_TRY(e->alloc(&e->d_Vp, c * 4096 * 128));
+  e->release(&e->d_Qp); SAMRS_TRY(e->alloc(&e->d_Qp, c * 4096 * 128));
+  e->release(&e->d_src); SAMRS_TRY(e->alloc(&e->d_src, c * 4096 * 256));
   e->mask_cap = cap;
   return 0;
 }
@@ -944,11 +940,7 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
   const int T = 5 + Ns, BT = B * T;
   if (T > 16) SAMRS_FAIL("decode: at most 11 sparse prompt tokens per prompt are supported");
   SAMRS_TRY(ensure_decoder_scratch(e, B));
-  static bool attr_done = false;
-  if (!attr_done) {
-    SAMRS_CUDA_OK(cudaFuncSetAttribute(tok_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr_done = true;
-  }
+  SAMRS_TRY(opt_in_smem(tok_self_attn_kernel, 64 * 1024));
   PromptParams pp;
   pp.gauss = e->gauss; pp.point_emb = e->point_emb; pp.not_a_point = e->not_a_point;
   pp.iou_token = e->iou_token; pp.mask_tokens = e->mask_tokens;
@@ -1087,13 +1079,8 @@ extern "C" void samrs_test_set_gemm_mode(int mode) { g_gemm_mode = mode; }
 extern "C" void samrs_test_set_attn_trace(void* dev_buf) { samrs::g_attn_dbg = dev_buf; }
 
 struct LaunchScope {
-  explicit LaunchScope(Engine* e) {
-    g_launch_counter = e ? &e->launches : nullptr;
-    g_prof = e ? &e->prof : nullptr;
-    g_splitk_ws = e ? e->splitk_ws : nullptr;
-    g_splitk_ws_floats = e ? e->splitk_ws_floats : 0;
-  }
-  ~LaunchScope() { g_launch_counter = nullptr; g_prof = nullptr; g_splitk_ws = nullptr; g_splitk_ws_floats = 0; }
+  explicit LaunchScope(Engine* e) { t_ctx = e ? &e->ctx : nullptr; }
+  ~LaunchScope() { t_ctx = nullptr; }
 };
 
 extern "C" {
@@ -1131,8 +1118,11 @@ int samrs_load_weights(void* engine, int n, const char* const* names, const void
   cudaSetDevice(e->device);
   SrcMap m;
   for (int i = 0; i < n; ++i) m[names[i]] = Src{static_cast<const float*>(dev_ptrs[i]), numel[i]};
-  LaunchScope ls(nullptr);
+  LaunchScope ls(e);
+  e->free_weights();                                   // loading again replaces the previous set instead of leaking it
+  e->loading_weights = true;
   int rc = load_weights_impl(e, m, static_cast<cudaStream_t>(stream));
+  e->loading_weights = false;
   if (rc == 0) e->weights_loaded = true;
   return set_err(e, rc);
 }
@@ -1251,17 +1241,27 @@ static void pil_coeffs(int in_size, int out_size, std::vector<int>& bounds, std:
 }
 
 static int resize_table(Engine* e, int in_size, int out_size, cudaStream_t st, const Engine::ResizeTab** out) {
-  for (const auto& t : e->resize_tabs)
-    if (t.in == in_size && t.out == out_size) { *out = &t; return 0; }
-  std::vector<int> b, k;
-  Engine::ResizeTab t{in_size, out_size, 0, nullptr, nullptr};
-  pil_coeffs(in_size, out_size, b, k, t.ksize);
-  if (e->alloc(&t.bounds, b.size()) != 0 || e->alloc(&t.kk, k.size()) != 0) return 1;
-  SAMRS_CUDA_OK(cudaMemcpyAsync(t.bounds, b.data(), b.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  SAMRS_CUDA_OK(cudaMemcpyAsync(t.kk, k.data(), k.size() * sizeof(int), cudaMemcpyHostToDevice, st));
-  SAMRS_CUDA_OK(cudaStreamSynchronize(st));          // the host vectors go out of scope; once per size pair
-  e->resize_tabs.push_back(t);
-  *out = &e->resize_tabs.back();
+  for (auto& t : e->resize_tabs)
+    if (t.in == in_size && t.out == out_size) { t.used = ++e->resize_clock; *out = &t; return 0; }
+  if (e->resize_tabs.size() >= 32) {
+    // datasets with free image sizes (DOTA, HRSC) would grow the cache without bound: drop the least recently used
+    // table (cudaFree waits for the kernels that may still read it; this only happens on the 33rd distinct size pair)
+    size_t lru = 0;
+    for (size_t i = 1; i < e->resize_tabs.size(); ++i)
+      if (e->resize_tabs[i].used < e->resize_tabs[lru].used) lru = i;
+    e->release(&e->resize_tabs[lru].bounds);
+    e->release(&e->resize_tabs[lru].kk);
+    e->resize_tabs.erase(e->resize_tabs.begin() + lru);
+  }
+  e->resize_tabs.emplace_back();
+  Engine::ResizeTab& t = e->resize_tabs.back();
+  t.in = in_size; t.out = out_size; t.ksize = 0; t.bounds = nullptr; t.kk = nullptr; t.used = ++e->resize_clock;
+  pil_coeffs(in_size, out_size, t.h_bounds, t.h_kk, t.ksize);
+  if (e->alloc(&t.bounds, t.h_bounds.size()) != 0 || e->alloc(&t.kk, t.h_kk.size()) != 0) return 1;
+  // the host vectors stay alive inside the table entry, so the copies need no synchronisation
+  SAMRS_CUDA_OK(cudaMemcpyAsync(t.bounds, t.h_bounds.data(), t.h_bounds.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(t.kk, t.h_kk.data(), t.h_kk.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  *out = &t;
   return 0;
 }
 
@@ -1281,6 +1281,7 @@ int samrs_resize_bilinear_u8(void* engine, const uint8_t* src_hwc, int H, int W,
     if (out_h != H) {                                   // a vertical pass follows: horizontal result goes to scratch
       const size_t need = size_t(H) * out_w * 3;
       if (need > e->resize_tmp_bytes) {
+        e->release(&e->resize_tmp);
         if (e->alloc(&e->resize_tmp, need) != 0) return set_err(e, 1);
         e->resize_tmp_bytes = need;
       }
@@ -1322,10 +1323,13 @@ int samrs_rle_encode(void* engine, const uint8_t* masks, const float* lowres, in
   const int HW32 = (H + 31) / 32;
   const size_t words = size_t(B > 0 ? B : 1) * HW32 * W;
   if (words > e->rle_packed_words) {
+    e->release(&e->rle_packed);
     if (e->alloc(&e->rle_packed, words) != 0) return set_err(e, 1);
     e->rle_packed_words = words;
   }
   if (B + 1 > e->rle_runs_cap) {
+    e->release(&e->rle_runs);
+    e->release(&e->rle_tstate);
     if (e->alloc(&e->rle_runs, size_t(B) + 1) != 0) return set_err(e, 1);
     if (e->alloc(&e->rle_tstate, (size_t(B) + 1) * RLE_THREADS * 2) != 0) return set_err(e, 1);
     e->rle_runs_cap = B + 1;
@@ -1359,33 +1363,48 @@ int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_id
   return 0;
 }
 
+int samrs_paint_masks(void* engine, const uint8_t* masks, const int* class_ids, int B, int H, int W, uint8_t* label_map, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  if (H < 1 || W < 1 || !masks || !class_ids || !label_map) return set_err(e, samrs::fail(__FILE__, __LINE__, "paint_masks: bad shape or null pointer"));
+  if (B < 1) return 0;
+  ProfScope ps(PC_EPILOGUE, static_cast<cudaStream_t>(stream));
+  const size_t HW = size_t(H) * W;
+  paint_masks_kernel<<<unsigned((HW / 4 + 256) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(masks, class_ids, B, HW, label_map);
+  count_launch();
+  if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "paint_masks launch failed"));
+  return 0;
+}
+
 int samrs_profile(void* engine, int enable, float* ms_by_category, int* launches_by_category, int ncat) {
   Engine* e = static_cast<Engine*>(engine);
   if (!e) return 1;
   cudaSetDevice(e->device);
   if (enable) {
-    for (auto& r : e->prof.recs) { e->prof.pool.push_back(r.a); e->prof.pool.push_back(r.b); }
-    e->prof.recs.clear();
-    e->prof.on = true;
+    for (auto& r : e->ctx.prof.recs) { e->ctx.prof.pool.push_back(r.a); e->ctx.prof.pool.push_back(r.b); }
+    e->ctx.prof.recs.clear();
+    e->ctx.prof.on = true;
     return 0;
   }
-  e->prof.on = false;
+  e->ctx.prof.on = false;
   if (cudaDeviceSynchronize() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "profile: device sync failed"));
   for (int i = 0; i < ncat; ++i) { if (ms_by_category) ms_by_category[i] = 0.f; if (launches_by_category) launches_by_category[i] = 0; }
-  for (auto& r : e->prof.recs) {
+  for (auto& r : e->ctx.prof.recs) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.a, r.b);
     if (r.cat < ncat) { if (ms_by_category) ms_by_category[r.cat] += ms; if (launches_by_category) launches_by_category[r.cat] += 1; }
-    e->prof.pool.push_back(r.a); e->prof.pool.push_back(r.b);
+    e->ctx.prof.pool.push_back(r.a); e->ctx.prof.pool.push_back(r.b);
   }
-  e->prof.recs.clear();
+  e->ctx.prof.recs.clear();
   return 0;
 }
 
 int samrs_launch_count(void* engine, int64_t* out) {
   Engine* e = static_cast<Engine*>(engine);
   if (!e || !out) return 1;
-  *out = e->launches;
+  *out = e->ctx.launches;
   return 0;
 }
 
@@ -1400,6 +1419,9 @@ void samrs_destroy(void* engine) {
   if (!e) return;
   cudaSetDevice(e->device);
   for (void* p : e->allocs) cudaFree(p);
+  for (void* p : e->weight_allocs) cudaFree(p);
+  for (auto& r : e->ctx.prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  for (cudaEvent_t ev : e->ctx.prof.pool) cudaEventDestroy(ev);
   delete e;
 }
 

@@ -33,6 +33,10 @@ struct GemmParams {
   int accumulate;       // fp32 output only: out += result (TMA reduce-add) instead of out = result
   int dbg_mode;         // tools only (results are garbage): bit0 skip TMA loads, bit1 skip MMAs, bit2 skip the epilogue
 };
+// Pipeline traces and the "remove one stage" experiments of tools/gemm_trace.py exist only in builds with
+// -DSAMRS_EXPERIMENTS (build.sh exp -> libsamrs_b200_exp.so); the product library compiles them away.
+#ifdef SAMRS_EXPERIMENTS
+constexpr bool kGemmExp = true;
 __device__ __forceinline__ void gemm_dbg(const GemmParams& p, int slot) {
   if (p.dbg != nullptr && blockIdx.x == 0 && slot < 4096) p.dbg[slot] = clock64();
 }
@@ -44,6 +48,11 @@ __device__ __forceinline__ void gemm_dbg_wall(const GemmParams& p, bool end) {
   if (end) atomicMax(p.dbg + 11, t); else atomicMin(p.dbg + 10, t);
   if (blockIdx.x == 0) p.dbg[end ? 13 : 12] = t;
 }
+#else
+constexpr bool kGemmExp = false;
+__device__ __forceinline__ void gemm_dbg(const GemmParams&, int) {}
+__device__ __forceinline__ void gemm_dbg_wall(const GemmParams&, bool) {}
+#endif
 
 constexpr int GEMM_BM = 128;
 constexpr int GEMM_BK = 64;   // one 128-byte swizzle atom of fp16
@@ -160,7 +169,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   for (int c = 0; c < NCH; ++c) {
     if (c < chunk_begin || c >= chunk_end) continue;
     if (n0 + c * 32 >= p.N) break;
-    const bool trc = (p.dbg != nullptr) && (threadIdx.x >> 5) == 4 && lane == 0 && nstaged < 32;
+    const bool trc = kGemmExp && (p.dbg != nullptr) && (threadIdx.x >> 5) == 4 && lane == 0 && nstaged < 32;
     const int tslot = 2048 + int(nstaged) * 8;
     if (trc) gemm_dbg(p, tslot + 0);
     uint32_t v[32];
@@ -303,7 +312,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::kStageBytes;
           uint8_t* sb = sa + GEMM_BM * 128;
-          if (p.dbg_mode & 1) {
+          if (kGemmExp && (p.dbg_mode & 1)) {
             if (elect_one()) mbar_arrive(&full[stage]);
           } else if (elect_one()) {
             mbar_expect_tx(&full[stage], Cfg::kStageBytes);
@@ -335,13 +344,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          if (kb < 40) gemm_dbg(p, 16 + ti * 64 + 2 + kb);
+          if (kGemmExp && kb < 40) gemm_dbg(p, 16 + ti * 64 + 2 + kb);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + GEMM_BM * 128;
           const uint64_t da = umma_desc_sw128(sa);
           const uint64_t db = umma_desc_sw128(sb);
           if (elect_one()) {
-            if (!(p.dbg_mode & 2)) {
+            if (!kGemmExp || !(p.dbg_mode & 2)) {
 #pragma unroll
               for (int k = 0; k < GEMM_BK / 16; ++k) {
                 // advance 16 fp16 (32 B) along K inside the swizzle atom: +2 in the (addr >> 4) field
@@ -380,7 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       if (warp == 4 && lane == 0) gemm_dbg(p, 16 + eti * 64 + 61);
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      if (!(p.dbg_mode & 4))
+      if (!kGemmExp || !(p.dbg_mode & 4))
         gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, bt, oscale, my_stage, nstaged, lane, bias_r, cb, ce);
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();

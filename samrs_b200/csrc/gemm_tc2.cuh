@@ -112,7 +112,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full[stage], phase);
           tc_fence_after();
-          if (kb < 40) gemm_dbg(p, 16 + ti * 64 + 2 + kb);
+          if (kGemmExp && kb < 40) gemm_dbg(p, 16 + ti * 64 + 2 + kb);
           const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
           const uint32_t sb = sa + GEMM_BM * 128;
           const uint64_t da = umma_desc_sw128(sa);

@@ -954,6 +954,28 @@ __global__ void upsample4_paint_kernel(const float* __restrict__ low /*[NB][256]
 }
 
 // ------------------------------------------------------------------------------------------------
+// Painter reduce over bool masks of any size (the driver's loop, main_sam_hbox_semantic.py:195-199, for tiles whose
+// original size is not 1024 x 1024: the masks come from the general-size postprocess).  One thread per 4 pixels scans
+// the boxes from the last to the first and stops at the first mask that is set: "highest box index wins" (SURVEY.md F1).
+// ------------------------------------------------------------------------------------------------
+__global__ void paint_masks_kernel(const uint8_t* __restrict__ masks /*[NB][H*W]*/, const int* __restrict__ labels, int NB,
+                                   size_t HW, uint8_t* __restrict__ canvas /*[H*W]*/) {
+  const size_t i0 = (size_t(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  if (i0 >= HW) return;
+  const int n = (HW - i0 >= 4) ? 4 : int(HW - i0);
+  uint32_t undecided = (1u << n) - 1u;
+  uint8_t cur[4];
+  for (int i = 0; i < n; ++i) cur[i] = canvas[i0 + i];
+  for (int b = NB - 1; b >= 0 && undecided; --b) {
+    const uint8_t* m = masks + size_t(b) * HW + i0;
+    const uint8_t lab = uint8_t(labels[b] & 0xFF);
+    for (int i = 0; i < n; ++i)
+      if (((undecided >> i) & 1) && m[i]) { cur[i] = lab; undecided &= ~(1u << i); }
+  }
+  for (int i = 0; i < n; ++i) canvas[i0 + i] = cur[i];
+}
+
+// ------------------------------------------------------------------------------------------------
 // Pillow-exact 8-bit bilinear image resize (ResizeLongestSide.apply_image, SA/utils/transforms.py:26-31 ->
 // PIL.Image.resize(BILINEAR) -> libImaging/Resample.c): two separable passes over uint8 HWC data with 22-bit fixed-point
 // taps; each pass accumulates 2^21 + sum(pixel * tap) in int32, shifts by 22 and clamps to [0, 255]; the horizontal pass

@@ -48,6 +48,8 @@ class Sam:
         if device.type != "cuda":
             raise RuntimeError("samrs_b200 has no CPU path: move the model to a CUDA device")
         from samrs_b200.engine import Engine
+        if device.index is None:                                   # "cuda" means the current device, as in torch
+            device = torch.device("cuda", torch.cuda.current_device())
         if self.engine is None or self.engine.device != device:
             self.engine = Engine(self.geometry, device)
             if self._state is not None:

@@ -57,7 +57,7 @@ class SamPredictor:
                 raise NotImplementedError("samrs_b200 encodes 8-bit images; got non-integral pixel values")
             img = rounded.to(torch.uint8)
         self.features = engine.encode(img.to(self.device), chw=not hwc)
-        self._engine_features = self.features
+        self._engine_features, self._engine_gen = self.features, engine.feature_gen
         self.is_image_set = True
 
     def predict(self, point_coords=None, point_labels=None, box=None, mask_input=None,
@@ -88,9 +88,11 @@ class SamPredictor:
         if not self.is_image_set:
             raise RuntimeError("An image must be set with .set_image(...) before mask prediction.")
         engine = self.model._require_engine()
-        if self.features is not self._engine_features:      # embedding assigned by hand
+        # the engine caches ONE image: re-install ours if the embedding was assigned by hand or if
+        # another predictor on the same Sam has encoded its own image since (the reference keeps features per predictor)
+        if self.features is not self._engine_features or engine.feature_gen != self._engine_gen:
             engine.set_features(self.features)
-            self._engine_features = self.features
+            self._engine_features, self._engine_gen = self.features, engine.feature_gen
         if boxes is not None and boxes.dim() == 1:
             boxes = boxes[None, :]
         low_res_masks, iou_predictions = engine.decode(
@@ -113,6 +115,7 @@ class SamPredictor:
         self.is_image_set = False
         self.features = None
         self._engine_features = None
+        self._engine_gen = -1
         self.orig_h = None
         self.orig_w = None
         self.input_h = None

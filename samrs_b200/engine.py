@@ -28,6 +28,7 @@ ABI = {
     "samrs_decode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "samrs_postprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "samrs_semantic_reduce": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    "samrs_paint_masks": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "samrs_resize_bilinear_u8": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),
     "samrs_rle_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, ctypes.c_longlong, _vp, _vp, _vp]),
     "samrs_profile": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _i]),
@@ -86,6 +87,9 @@ class Engine:
         if rc != 0:
             raise RuntimeError("samrs_create failed: " + self._lib.samrs_last_error(None).decode())
         self.weights_loaded = False
+        # the image embedding lives in the engine, not in whoever called encode(): every change of it bumps this counter so
+        # that a predictor can tell whether the engine still holds ITS image (two predictors may share one Sam)
+        self.feature_gen = 0
 
     # -- helpers -----------------------------------------------------------------
     def _check(self, rc: int, what: str) -> None:
@@ -123,6 +127,7 @@ class Engine:
             self._check(self._lib.samrs_load_weights(self._h, n, c_names, c_ptrs, c_numel, _stream(self.device)), "load_weights")
             torch.cuda.current_stream(self.device).synchronize()   # staged tensors are freed on return
         self.weights_loaded = True
+        self.feature_gen += 1                                      # a reload invalidates the cached image embedding
 
     def encode(self, image_u8: torch.Tensor, chw: bool = False) -> torch.Tensor:
         """uint8 image on the device, HWC (or CHW) with H,W <= 1024 -> features (1,256,64,64) fp32."""
@@ -131,6 +136,7 @@ class Engine:
         feats = torch.empty((1, 256, 64, 64), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             self._check(self._lib.samrs_encode(self._h, img.data_ptr(), H, W, int(chw), feats.data_ptr(), _stream(self.device)), "encode")
+        self.feature_gen += 1
         return feats
 
     def set_features(self, features: torch.Tensor) -> None:
@@ -138,6 +144,7 @@ class Engine:
         assert tuple(f.shape) == (1, 256, 64, 64)
         with torch.cuda.device(self.device):
             self._check(self._lib.samrs_set_features(self._h, f.data_ptr(), _stream(self.device)), "set_features")
+        self.feature_gen += 1
 
     def decode(self, boxes: Optional[torch.Tensor] = None, point_coords: Optional[torch.Tensor] = None,
                point_labels: Optional[torch.Tensor] = None, mask_input: Optional[torch.Tensor] = None,
@@ -189,6 +196,21 @@ class Engine:
         with torch.cuda.device(self.device):
             self._check(self._lib.samrs_semantic_reduce(self._h, low.data_ptr(), ids.data_ptr(), B, label_map.data_ptr(),
                                                         label_map.shape[0], label_map.shape[1], _stream(self.device)), "semantic_reduce")
+        return label_map
+
+    def paint_masks(self, masks: torch.Tensor, class_ids: torch.Tensor, label_map: torch.Tensor) -> torch.Tensor:
+        """In-place painter reduce of (B,[1,]H,W) bool masks into an (H,W) uint8 label map: the general-size companion of
+        `semantic_reduce` (tiles whose original size is not 1024 x 1024)."""
+        m = masks.view(torch.uint8) if masks.dtype == torch.bool else masks
+        m = self._dev(m, torch.uint8)
+        ids = self._dev(class_ids, torch.int32)
+        H, W = int(label_map.shape[0]), int(label_map.shape[1])
+        assert label_map.dtype == torch.uint8 and label_map.is_contiguous() and label_map.device == self.device
+        assert m.shape[-2:] == (H, W)
+        B = m.numel() // (H * W)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_paint_masks(self._h, m.data_ptr(), ids.data_ptr(), B, H, W, label_map.data_ptr(),
+                                                    _stream(self.device)), "paint_masks")
         return label_map
 
     def resize_image(self, image: torch.Tensor, out_hw: Sequence[int]) -> torch.Tensor:

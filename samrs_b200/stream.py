@@ -68,39 +68,215 @@ def max_over_ranks(value: float, device, group=None) -> float:
     return float(t.item())
 
 
+def _decode_chunks(predictor, engine, boxes_dev: torch.Tensor, original_hw, chunk: int):
+    """predict_torch's prompt path without the full-resolution bool masks: transformed boxes -> low-res logits per chunk."""
+    for s in range(0, boxes_dev.shape[0], chunk):
+        tb = predictor.transform.apply_boxes_torch(boxes_dev[s:s + chunk], original_hw)
+        low, _ = engine.decode(boxes=tb, multimask_output=False)
+        yield s, low
+
+
+def tile_outputs(predictor, engine, image: np.ndarray, boxes: torch.Tensor, labels: torch.Tensor, canvas: torch.Tensor,
+                 chunk: int = 20, instance: bool = True, capacity_per_mask: int = 65536):
+    """Both products of one iteration of the driver's per-image loop (`main_sam_hbox_semantic.py:155-204`) from ONE
+    encode: the label map (painter reduce) in `canvas` and, if `instance`, the run-length payload of every mask.
+
+    Everything is enqueued on the current stream; nothing is copied to the host.  Returns `(canvas, payload)` with
+    `payload = [(counts, offsets, area, n_masks, capacity), ...]` per chunk (CUDA tensors).  1024 x 1024 tiles use the
+    fused kernels (upsample + threshold + paint / + RLE straight from the 256 x 256 logits); other sizes go through the
+    general postprocess and paint / encode the bool masks."""
+    predictor.set_image(image)
+    H, W = int(image.shape[0]), int(image.shape[1])
+    fused = (H, W) == (1024, 1024)
+    canvas.fill_(255)
+    payload = []
+    bdev = boxes.to(predictor.device, non_blocking=True)
+    ldev = labels.to(device=predictor.device, dtype=torch.int32, non_blocking=True)
+    for s, low in _decode_chunks(predictor, engine, bdev, (H, W), chunk):
+        n = low.shape[0]
+        if fused:
+            engine.semantic_reduce(low, ldev[s:s + n], canvas)
+            if instance:
+                cap = n * capacity_per_mask
+                payload.append(engine.rle_encode(low_res=low, capacity=cap) + (n, cap))
+        else:
+            masks = engine.postprocess(low, predictor.input_size, (H, W))
+            engine.paint_masks(masks, ldev[s:s + n], canvas)
+            if instance:
+                cap = n * capacity_per_mask
+                payload.append(engine.rle_encode(masks=masks, capacity=cap) + (n, cap))
+    return canvas, payload
+
+
 def semantic_tile(predictor, engine, image: np.ndarray, boxes: torch.Tensor, labels: torch.Tensor, canvas: torch.Tensor,
                   chunk: int = 20) -> torch.Tensor:
-    """One iteration of the driver's per-image loop (`main_sam_hbox_semantic.py:155-199`) with the painter reduce
-    fused on the device: set_image, predict_torch in chunks of `chunk` boxes, label map into `canvas`."""
-    predictor.set_image(image)
-    canvas.fill_(255)
-    for s in range(0, boxes.shape[0], chunk):
-        tb = predictor.transform.apply_boxes_torch(boxes[s:s + chunk], image.shape[:2])
-        _, _, low = predictor.predict_torch(None, None, boxes=tb, mask_input=None, multimask_output=False)
-        engine.semantic_reduce(low, labels[s:s + chunk], canvas)
-    return canvas
+    """The semantic branch alone: set_image, chunks of `chunk` boxes, label map into `canvas`."""
+    return tile_outputs(predictor, engine, image, boxes, labels, canvas, chunk, instance=False)[0]
 
 
 def instance_tile(predictor, engine, image: np.ndarray, boxes: torch.Tensor, labels, categories=None, chunk: int = 20):
-    """The instance branch of the same loop (`main_sam_hbox_semantic.py:183-204`): per box a COCO-RLE mask, its area and the
-    annotation fields.  The masks never leave the device: every chunk's low-res logits go through `Engine.rle_encode`
-    (fused upsample + threshold + run-length encoding), and only the runs (tens of KiB per tile) are copied back."""
+    """The instance branch alone (`main_sam_hbox_semantic.py:183-204`): per box a COCO-RLE mask, its area and the
+    annotation fields.  The masks never leave the device; only the runs (tens of KiB per tile) are copied back."""
     from . import rle as host_rle
-    if image.shape[0] != 1024 or image.shape[1] != 1024:
-        raise ValueError("instance_tile: the fused low-res path needs a 1024x1024 tile")
-    predictor.set_image(image)
-    records = []
-    for s in range(0, boxes.shape[0], chunk):
-        tb = predictor.transform.apply_boxes_torch(boxes[s:s + chunk], image.shape[:2])
-        _, _, low = predictor.predict_torch(None, None, boxes=tb, mask_input=None, multimask_output=False)
-        n = low.shape[0]
-        cap = n * 16384
-        while True:
-            counts, offsets, area = engine.rle_encode(low_res=low, capacity=cap)
-            total = int(offsets[-1])                     # synchronises: the host needs the payload anyway
-            if total <= cap:
-                break
-            cap = total
-        records += host_rle.instance_records(counts, offsets, area, 1024, 1024, boxes[s:s + chunk].detach().cpu().numpy(),
-                                             [int(v) for v in labels[s:s + chunk]], categories)
+    H, W = int(image.shape[0]), int(image.shape[1])
+    canvas = torch.empty((H, W), dtype=torch.uint8, device=predictor.device)
+    lab_t = torch.as_tensor([int(v) for v in labels], dtype=torch.int32)
+    _, payload = tile_outputs(predictor, engine, image, boxes, lab_t, canvas, chunk, instance=True)
+    return _records_from_payload(engine, payload, H, W, boxes.detach().cpu().numpy(), [int(v) for v in labels], categories, None)
+
+
+def _records_from_payload(engine, payload, H, W, boxes_np, labels, categories, rboxes_np, low_keep=None):
+    from . import rle as host_rle
+    records, s = [], 0
+    for (counts, offsets, area, n, cap) in payload:
+        total = int(offsets[-1])                         # synchronises: the host needs the payload anyway
+        if total > cap:
+            raise RuntimeError(f"rle: {total} runs exceed the capacity of {cap}; raise capacity_per_mask")
+        records += host_rle.instance_records(counts, offsets, area, H, W, boxes_np[s:s + n], labels[s:s + n], categories,
+                                             rboxes=None if rboxes_np is None else rboxes_np[s:s + n])
+        s += n
     return records
+
+
+# ------------------------------------------------------------------------------------------------ the tile stream
+class TileJob:
+    """One image of a driver's `for file in files` loop: name, pixels (HWC uint8 array, or a callable returning one so the
+    decode happens on a loader thread), horizontal boxes in original-image pixels, class ids, optional rotated boxes."""
+
+    __slots__ = ("name", "image", "boxes", "labels", "rboxes")
+
+    def __init__(self, name, image, boxes, labels, rboxes=None):
+        self.name, self.image, self.boxes, self.labels, self.rboxes = name, image, boxes, labels, rboxes
+
+
+def run(predictor, jobs: Iterable, save_dir: str = None, mapping=None, categories: Sequence[str] = None, chunk: int = 20,
+        instance: bool = True, writer_threads: int = 4, loader_threads: int = 2, depth: int = 4, on_tile=None) -> Dict[str, float]:
+    """The per-rank loop that replaces `main_sam_hbox_semantic.py:110-216` (and the rhbox variant when jobs carry rboxes).
+
+      loader threads  materialise each job's image into a pinned ring slot (JPEG / PNG decode off the GPU thread)
+      this thread     H2D + encode ONCE + decode in the driver's chunks + painter + RLE, all on the current stream, then
+                      asynchronous D2H of the label map and the runs into the slot's pinned buffers and an event
+      finisher thread waits for the slot's event, builds the instance records and hands the tile to
+      writer threads  `writers.save_tile` (gray / color PNG + pickle), the reference's on-disk contract
+    Slots are recycled in order, so at most `depth` tiles are in flight and the GPU thread never waits for a writer
+    unless the writers fall `depth` tiles behind.  Returns counters (`tiles`, `masks`, `seconds`)."""
+    import queue
+    import threading
+    import time
+    from concurrent.futures import ThreadPoolExecutor
+
+    from . import writers
+    engine = predictor.model._require_engine()
+    device = predictor.device
+    jobs = iter(jobs)
+    ready: "queue.Queue" = queue.Queue(maxsize=depth)
+    free_slots: "queue.Queue" = queue.Queue()
+    done_q: "queue.Queue" = queue.Queue()
+    errors: List[BaseException] = []
+    lock = threading.Lock()
+
+    class Slot:
+        def __init__(self):
+            self.img = None                                   # pinned uint8 HWC, grown on demand
+            self.canvas_h = None
+            self.canvas_d = None
+            self.event = torch.cuda.Event()
+            self.host_payload = []
+
+    for _ in range(depth):
+        free_slots.put(Slot())
+
+    def loader():
+        try:
+            while True:
+                with lock:
+                    job = next(jobs, None)
+                if job is None:
+                    break
+                img = job.image() if callable(job.image) else job.image
+                img = np.ascontiguousarray(img)
+                slot = free_slots.get()
+                if slot.img is None or slot.img.numel() < img.size:
+                    slot.img = torch.empty(img.size, dtype=torch.uint8).pin_memory()
+                view = slot.img[: img.size].view(*img.shape)
+                view.numpy()[...] = img
+                ready.put((job, slot, view))
+        except BaseException as ex:                            # surfaced by the GPU thread
+            errors.append(ex)
+        finally:
+            ready.put(None)
+
+    def finisher(pool):
+        while True:
+            item = done_q.get()
+            if item is None:
+                break
+            job, slot, H, W, payload_h = item
+            try:
+                slot.event.synchronize()
+                label_map = slot.canvas_h[: H * W].view(H, W).numpy().copy()
+                records = []
+                if instance:
+                    from . import rle as host_rle
+                    s = 0
+                    boxes_np = np.asarray(job.boxes)
+                    rb = None if job.rboxes is None else np.asarray(job.rboxes)
+                    for (counts, offsets, area, n, cap) in payload_h:
+                        if int(offsets[-1]) > cap:
+                            raise RuntimeError(f"rle: {int(offsets[-1])} runs exceed the capacity of {cap}")
+                        records += host_rle.instance_records(counts, offsets, area, H, W, boxes_np[s:s + n],
+                                                             [int(v) for v in job.labels[s:s + n]], categories,
+                                                             rboxes=None if rb is None else rb[s:s + n])
+                        s += n
+                free_slots.put(slot)                           # pinned buffers are copied out: recycle the slot
+                if on_tile is not None:
+                    on_tile(job, label_map, records)
+                if save_dir is not None:
+                    pool.submit(writers.save_tile, save_dir, job.name, label_map, mapping, records)
+            except BaseException as ex:
+                errors.append(ex)
+                free_slots.put(slot)
+
+    loaders = [threading.Thread(target=loader, daemon=True) for _ in range(max(1, loader_threads))]
+    pool = ThreadPoolExecutor(max_workers=max(1, writer_threads))
+    fin = threading.Thread(target=finisher, args=(pool,), daemon=True)
+    for t in loaders:
+        t.start()
+    fin.start()
+    tiles = masks = 0
+    t0 = time.time()
+    live = len(loaders)
+    try:
+        while live:
+            item = ready.get()
+            if item is None:
+                live -= 1
+                continue
+            if errors:
+                break
+            job, slot, view = item
+            H, W = int(view.shape[0]), int(view.shape[1])
+            if slot.canvas_d is None or slot.canvas_d.numel() < H * W:
+                slot.canvas_d = torch.empty(H * W, dtype=torch.uint8, device=device)
+                slot.canvas_h = torch.empty(H * W, dtype=torch.uint8).pin_memory()
+            canvas = slot.canvas_d[: H * W].view(H, W)
+            boxes = torch.as_tensor(np.asarray(job.boxes))
+            labels = torch.as_tensor(np.asarray(job.labels))
+            _, payload = tile_outputs(predictor, engine, view.numpy(), boxes, labels, canvas, chunk, instance)
+            slot.canvas_h[: H * W].copy_(canvas.view(-1), non_blocking=True)
+            payload_h = []
+            for (counts, offsets, area, n, cap) in payload:
+                # only offsets[-1] runs are meaningful, but the host learns that number with the copy: ship a bounded slab
+                payload_h.append((counts.to("cpu", non_blocking=True), offsets.to("cpu", non_blocking=True),
+                                  area.to("cpu", non_blocking=True), n, cap))
+            slot.event.record(torch.cuda.current_stream(device))
+            done_q.put((job, slot, H, W, payload_h))
+            tiles += 1
+            masks += int(boxes.shape[0])
+    finally:
+        done_q.put(None)
+        fin.join()
+        pool.shutdown(wait=True)
+    if errors:
+        raise errors[0]
+    return {"tiles": tiles, "masks": masks, "seconds": time.time() - t0}
