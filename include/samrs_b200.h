@@ -90,6 +90,11 @@ int samrs_rle_encode(void* engine, const uint8_t* masks, const float* lowres, in
  * 6 decode call, 7 post-processing / painter. */
 int samrs_profile(void* engine, int enable, float* ms_by_category, int* launches_by_category, int ncat);
 
+/* CUDA graphs: by default the engine captures the encode body and each decode shape on their second call and replays the
+ * graphs afterwards (launches that touch caller-owned buffers stay outside; profiling runs eagerly).  enable = 0 drops
+ * the graphs and launches every kernel directly. */
+int samrs_set_graphs(void* engine, int enable);
+
 /* kernels launched by this engine since creation (bench.py's gpu_launches). */
 int samrs_launch_count(void* engine, int64_t* count_out);
 

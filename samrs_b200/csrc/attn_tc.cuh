@@ -33,6 +33,7 @@ struct AttnParams {
   int heads;
   int num_qtiles;       // windowed: 25 windows * 2 halves; global: 32
   float scale_log2e;    // hd^-0.5 * log2(e)
+  float rel_scale;      // windowed blocks: 1 / scale_log2e, applied to G = q . log2e [rel_pos_h ; rel_pos_w]^T before it becomes R
   unsigned long long* dbg;   // optional pipeline trace of CTA 0 (tools/attn_trace.py)
   int pv_split;         // attention v2, head dim 80: 1 = issue P.V as an N=64 and an N=16 MMA per k-step (first version), 0 = one N=80 MMA
 };

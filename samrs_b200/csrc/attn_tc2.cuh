@@ -16,8 +16,15 @@
 //     one-hot matrix in shared memory (global: E[k][kw'] = [k mod 64 == kw'], the two relh terms of a key tile stay
 //     scalar; windowed: E[k][kh'] = [k div 14 == kh'], E[k][14+kw'] = [k mod 14 == kw']).  One extra MMA per key tile
 //     (K = 64 / 32) replaces a load + add per score, which halves the instruction count of both softmax passes.
+//   * windowed blocks compute the rel-pos terms themselves: G = Q . T^T with T = log2e [rel_pos_h ; rel_pos_w] (27 + 27
+//     rows, resident in shared memory) is one more N = 64 MMA per query tile into the still-unused S columns; the row's
+//     thread reads its 54 values, selects the 14 + 14 its query position needs (a 4-stage barrel shift: no dynamic
+//     register indexing, no memory), scales them and writes them as the fp16 operand R.  The separate head-batched
+//     rel-pos GEMM and its [heads][4096][64] table (28 launches, 8 MB written and gathered per layer) are gone; global
+//     blocks (4 of 32) keep the GEMM + gather, whose table rows depend on the key tile.
 // TMEM (512 columns): warpgroup w owns columns [256w, 256w+256): S at +0 (208 or 128 fp32 columns), P aliased on
-// S's first half, O at +112 (windowed: inside the dead upper half of S) or +128 (global), R at +208.
+// S's first half, O at +112 (windowed: inside the dead upper half of S) or +128 (global), R at +208; windowed G at +0
+// (read and replaced by R before the S MMA is issued).
 #pragma once
 #include <type_traits>
 
@@ -39,7 +46,9 @@ struct Attn2Cfg {
   static constexpr int R_OFF = 208;                          // TMEM column of the packed fp16 rel-pos operand R
   static constexpr int RK = (NKT > 1) ? 64 : 32;             // K extent of the bias MMA (kw' | kh',kw')
   static constexpr int E_BYTES = SN * 128;                   // one-hot matrix E: SN key rows x 64 fp16 (SW128 atom rows)
-  static constexpr int kSmemBytes = 2 * Q_TILE_BYTES + 2 * KV_STAGES * KV_BYTES + E_BYTES + 1024 + 256;
+  static constexpr int T_ROWS = 64;                          // windowed: rel-pos table rows (27 + 27, zero padded)
+  static constexpr int T_BYTES = (NKT == 1) ? NATOM * T_ROWS * 128 : 0;
+  static constexpr int kSmemBytes = 2 * Q_TILE_BYTES + 2 * KV_STAGES * KV_BYTES + E_BYTES + T_BYTES + 1024 + 256;
   static_assert(SN % 16 == 0 && SN <= 208, "bad S tile");
   static_assert(O_OFF >= SN / 2 && O_OFF + HD <= 256, "O must not overlap P");
 };
@@ -86,7 +95,8 @@ __device__ __forceinline__ float ex2_mixed(float x) {
 
 template <int HD, int BX, int QBY, int KBY, int NKT>
 __global__ void __launch_bounds__(384, 1)
-attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const AttnParams p) {
+attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV,
+                const __grid_constant__ CUtensorMap tmT /*windowed: rel-pos table [64][HD] fp16*/, const AttnParams p) {
   using C = Attn2Cfg<HD, BX, QBY, KBY, NKT>;
   constexpr int NATOM = C::NATOM, SN = C::SN, KR = C::KR, QR = C::QR, ST = C::KV_STAGES;
   extern __shared__ uint8_t smem_raw[];
@@ -95,7 +105,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint8_t* sK = sQ + 2 * C::Q_TILE_BYTES;
   uint8_t* sV = sK + ST * C::KV_BYTES;
   uint8_t* sE = sV + ST * C::KV_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sE + C::E_BYTES);
+  uint8_t* sT = sE + C::E_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sT + C::T_BYTES);
   uint64_t* q_full = bars + 0;
   uint64_t* q_empty = bars + 1;
   uint64_t* k_full = bars + 2;        // [2]
@@ -107,7 +118,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   uint64_t* o_full = bars + 14;       // [2] per warpgroup: last PV of the unit done
   uint64_t* o_free = bars + 16;       // [2] per warpgroup, 128 arrivals: O has been read, S/O region reusable
   uint64_t* r_full = bars + 18;       // [2] per warpgroup, 128 arrivals: this unit's R operand is in TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 20);
+  uint64_t* g_full = bars + 20;       // [2] per warpgroup (windowed): G = Q T^T is in TMEM
+  uint64_t* t_full = bars + 22;       // windowed: the rel-pos table has landed in shared memory (once per CTA)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,6 +146,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
     tma_prefetch_desc(&tmKV);
+    if (NKT == 1) tma_prefetch_desc(&tmT);
   }
   if (warp == 1 && lane == 0) {
     mbar_init(q_full, 1);
@@ -147,7 +161,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(&o_full[i], 1);
       mbar_init(&o_free[i], 128);
       mbar_init(&r_full[i], 128);
+      mbar_init(&g_full[i], 1);
     }
+    mbar_init(t_full, 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<512>(tmem_slot);
@@ -183,6 +199,14 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     {
       uint32_t qph = 0, kst = 0, kph = 0, vst = 0, vph = 0;
       int ui = 0;
+      if (NKT == 1 && int(blockIdx.x) < num_units) {
+        if (elect_one()) {
+          mbar_expect_tx(t_full, C::T_BYTES);
+#pragma unroll
+          for (int a = 0; a < NATOM; ++a) tma_load_2d(sT + a * C::T_ROWS * 128, &tmT, t_full, a * 64, 0);
+        }
+        __syncwarp();
+      }
       for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
         int head, qy0, qy1, x0, ky0;
         unit_coords(unit, head, qy0, qy1, x0, ky0);
@@ -231,7 +255,22 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       constexpr uint32_t idesc_o16 = umma_idesc_f16(128, 16, 0, 1);
       constexpr uint32_t idesc_o80 = umma_idesc_f16(128, 80, 0, 1);
       uint32_t qph = 0, kst = 0, kph = 0, vst = 0, vph = 0, pph[2] = {0, 0}, fph[2] = {0, 0}, rph = 0;
-      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aE = smem_u32(sE);
+      const uint32_t aQ = smem_u32(sQ), aK = smem_u32(sK), aV = smem_u32(sV), aE = smem_u32(sE), aT = smem_u32(sT);
+      constexpr uint32_t idesc_g = umma_idesc_f16(128, 64, 0, 0);
+      auto issue_g = [&](int w) {                       // windowed: G_w = Q_w T^T into the (still unused) first S columns
+        const uint32_t d = tmem_base + uint32_t(w * 256);
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k) {
+            const uint32_t a = aQ + w * C::Q_TILE_BYTES + (k / 4) * (128 * 128) + (k % 4) * 32;
+            const uint32_t b = aT + (k / 4) * (C::T_ROWS * 128) + (k % 4) * 32;
+            tc_mma_f16(d, umma_desc_sw128(a), umma_desc_sw128(b), idesc_g, k != 0);
+          }
+          tc_commit(&g_full[w]);
+        }
+        __syncwarp();
+      };
+      if (NKT == 1 && int(blockIdx.x) < num_units) mbar_wait(t_full, 0);
       auto issue_s = [&](int w) {                       // S_w = Q_w K^T into warpgroup w's columns
         const uint32_t d = tmem_base + uint32_t(w * 256);
         if (elect_one()) {
@@ -275,12 +314,23 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_wait(q_full, qph);
         qph ^= 1;
         attn_dbg(p, 64 * ui + 9);
+        if (NKT == 1) {
+          tc_fence_after();
+          for (int w = 0; w < 2; ++w) {                 // the warpgroup has read the previous unit's O (aliases S and G)
+            mbar_wait(&o_free[w], fph[w] ^ 1);
+            fph[w] ^= 1;
+            tc_fence_after();
+            issue_g(w);
+          }
+        }
         mbar_wait(&k_full[kst], kph);
         tc_fence_after();
         attn_dbg(p, 64 * ui + 10);
         for (int w = 0; w < 2; ++w) {                   // the warpgroup has read the previous unit's O (aliases S)
-          mbar_wait(&o_free[w], fph[w] ^ 1);
-          fph[w] ^= 1;
+          if (NKT > 1) {
+            mbar_wait(&o_free[w], fph[w] ^ 1);
+            fph[w] ^= 1;
+          }
           mbar_wait(&r_full[w], rph);                   // ... and has stored this unit's R operand
           tc_fence_after();
           issue_s(w);
@@ -322,7 +372,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const uint32_t wg_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(w * 256);
     constexpr int NP = (BX == 64) ? 256 : 64;
     constexpr int SS = BX;
-    uint32_t sph = 0, oph = 0;
+    uint32_t sph = 0, oph = 0, gph = 0;
     int ui = 0;
     const bool tr = (r == 0);
     // rel-pos terms of this thread's query row for unit `un`, divided by the score scale (the accumulator is scaled
@@ -335,7 +385,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int ty = qy + r / BX, tx = x0 + r % BX;
       const bool valid = (r < QR) && ty < 64 && tx < 64;
       const int qh = qy - ky0 + r / BX, qw = r % BX;
-      if (NKT > 1) {
+      if constexpr (NKT > 1) {
         // the rel-pos GEMM's epilogue wrote fp16(G / scale_log2e), i.e. the entries of the bias operand R themselves
         const __half* rrow = p.rel16 + (size_t(head) * 4096 + (valid ? ty * 64 + tx : 0)) * NP;
         const __half zero = __float2half_rn(0.f);
@@ -346,25 +396,9 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           __half2 h = __halves2half2(a0, a1);
           rk_next[i] = *reinterpret_cast<uint32_t*>(&h);
         }
-      } else {
-        // windowed: the GEMM epilogue already produced fp16(G / scale_log2e); gather this row's 14 + 14 entries
-        const __half* rrow = p.rel16 + (size_t(head) * 4096 + (valid ? ty * 64 + tx : 0)) * NP;
-        const __half zero = __float2half_rn(0.f);
-        __half rv[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) rv[i] = zero;
-#pragma unroll
-        for (int i = 0; i < KBY; ++i) rv[i] = valid ? __ldg(rrow + qh + (SS - 1) - i) : zero;
-#pragma unroll
-        for (int i = 0; i < BX; ++i) rv[KBY + i] = valid ? __ldg(rrow + (2 * SS - 1) + qw + (SS - 1) - i) : zero;
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          __half2 h = __halves2half2(rv[2 * i], rv[2 * i + 1]);
-          rk_next[i] = *reinterpret_cast<uint32_t*>(&h);
-        }
       }
     };
-    if (int(blockIdx.x) < num_units) load_rk(blockIdx.x);
+    if (NKT > 1 && int(blockIdx.x) < num_units) load_rk(blockIdx.x);
     for (int unit = blockIdx.x; unit < num_units; unit += gridDim.x, ++ui) {
       int head, qy0, qy1, x0, ky0;
       unit_coords(unit, head, qy0, qy1, x0, ky0);
@@ -375,8 +409,43 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int token = ty * 64 + tx;
       const __half* relrow = p.rel16 + (size_t(head) * 4096 + (valid ? token : 0)) * NP;
       const int qh = qy - ky0 + r / BX;
-      // this row's packed rel-pos operand R was prefetched during the previous unit (rk_next): store it to tensor memory
-      if constexpr (C::RK == 64) tmem_st32(wg_addr + C::R_OFF, rk_next); else tmem_st16(wg_addr + C::R_OFF, rk_next);
+      if constexpr (NKT > 1) {
+        // this row's packed rel-pos operand R was prefetched during the previous unit (rk_next): store it to tensor memory
+        tmem_st32(wg_addr + C::R_OFF, rk_next);
+      } else {
+        // windowed: G = q . log2e [rel_pos_h ; rel_pos_w]^T (54 values) is in this row's first 64 S columns.  The query at
+        // window position (qh, qw) needs rel_h[kh] = G[qh - kh + 13] and rel_w[kw] = G[27 + qw - kw + 13]: shift each
+        // 27-entry half down by qh / qw with a 4-stage barrel shifter (warp-divergent selects, no indexing), reverse,
+        // scale by 1 / (scale log2e) (the accumulator is multiplied by scale log2e afterwards) and pack to fp16.
+        mbar_wait(&g_full[w], gph);
+        gph ^= 1;
+        tc_fence_after();
+        uint32_t rk[16];
+        rk[14] = 0u;
+        rk[15] = 0u;
+        // one 27-entry half at a time (32 live registers): columns [0,27) = rel_pos_h terms, [27,54) = rel_pos_w terms
+        static_for<0, 2, 1>([&](auto hc) {
+          constexpr int half = decltype(hc)::value;
+          uint32_t gv[32];
+          tmem_ld32(wg_addr + half * 27, gv);
+          tc_wait_ld();
+          const int sft = half ? (r % BX) : qh;
+#pragma unroll
+          for (int b = 8; b >= 1; b >>= 1) {             // largest shift first: every stage reads entries that the earlier
+            const bool m = (sft & b) != 0;               // (larger) stages have already brought into range
+#pragma unroll
+            for (int j = 0; j < 14 + 8; ++j)             // after all stages only entries 0..13 are used
+              if (j + b < 27) gv[j] = m ? gv[j + b] : gv[j];
+              else gv[j] = m ? 0u : gv[j];
+          }
+#pragma unroll
+          for (int i = 0; i < 7; ++i) {                  // operand columns half*14 + {2i, 2i+1} <- shifted entries 13-2i, 12-2i
+            __half2 h = __floats2half2_rn(__uint_as_float(gv[13 - 2 * i]) * p.rel_scale, __uint_as_float(gv[12 - 2 * i]) * p.rel_scale);
+            rk[half * 7 + i] = *reinterpret_cast<uint32_t*>(&h);
+          }
+        });
+        tmem_st16(wg_addr + C::R_OFF, rk);
+      }
       tc_wait_st();
       tc_fence_before();
       mbar_arrive(&r_full[w]);
@@ -474,7 +543,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         mbar_arrive(&p_full[w]);
         if (tr && j == 0) attn_dbg(p, 64 * ui + 24 + 10 * w);
       }
-      if (unit + int(gridDim.x) < num_units) load_rk(unit + gridDim.x);    // prefetch the next unit's R while PV runs
+      if (NKT > 1 && unit + int(gridDim.x) < num_units) load_rk(unit + gridDim.x);    // prefetch the next unit's R while PV runs
       // O complete: normalise and write the fp16 output row
       mbar_wait(&o_full[w], oph);
       oph ^= 1;

@@ -328,6 +328,22 @@ struct Engine {
   std::vector<void*> weight_allocs;      // everything load_weights_impl allocates: freed when weights are loaded again
   bool loading_weights = false;
   bool weights_loaded = false, image_set = false;
+  // CUDA graphs of the two static-shape launch sequences (encode body; decode body per (prompts, tokens, flags)): the first
+  // call of a shape runs eagerly (it also opts the kernels into large shared memory), the second captures on `cap_stream`,
+  // later calls replay the instantiated graph into the caller's stream.  Kernels that touch caller-owned pointers (image
+  // in, features / logits / IoU out, prompts) stay outside the graphs.  Profiling (per-launch events) runs eagerly.
+  struct GraphEntry { cudaGraphExec_t exec = nullptr; int launches = 0; int eager_runs = 0; };
+  bool graphs_enabled = true;
+  cudaStream_t cap_stream = nullptr;
+  GraphEntry enc_graph;
+  std::unordered_map<uint64_t, GraphEntry> dec_graphs;
+  void drop_graphs() {
+    if (enc_graph.exec) cudaGraphExecDestroy(enc_graph.exec);
+    enc_graph = GraphEntry();
+    for (auto& kv : dec_graphs)
+      if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+    dec_graphs.clear();
+  }
 
   // encoder weights
   __half* w_patch = nullptr; float* b_patch = nullptr; float* pos_embed = nullptr;
@@ -390,11 +406,13 @@ struct Engine {
     void* q = reinterpret_cast<void*>(*p);
     for (size_t i = 0; i < allocs.size(); ++i)
       if (allocs[i] == q) { allocs[i] = allocs.back(); allocs.pop_back(); cudaFree(q); break; }
+    drop_graphs();                                   // captured launches may hold the old address
     *p = nullptr;
   }
   void free_weights() {
     if (weight_allocs.empty()) return;
     cudaDeviceSynchronize();
+    drop_graphs();
     for (void* q : weight_allocs) cudaFree(q);
     weight_allocs.clear();
     weights_loaded = image_set = false;
@@ -404,6 +422,42 @@ struct Engine {
 static int set_err(Engine* e, int rc) {
   if (rc != 0 && e) e->err = g_last_error;
   return rc;
+}
+
+// Runs `body(stream)` eagerly on `st`, or - from the third call of this shape on - replays its captured CUDA graph in `st`.
+template <class F>
+static int run_graphed(Engine* e, Engine::GraphEntry& ge, cudaStream_t st, F&& body) {
+  const bool can = e->graphs_enabled && e->cap_stream != nullptr && t_ctx != nullptr && !t_ctx->prof.on;
+  if (!can) return body(st);
+  if (ge.eager_runs == 0) {                            // first call: eager (kernel attributes, lazily built tables)
+    ge.eager_runs = 1;
+    return body(st);
+  }
+  if (ge.exec == nullptr) {
+    const int64_t l0 = t_ctx->launches;
+    cudaGraph_t g = nullptr;
+    int rc = 1;
+    if (cudaStreamBeginCapture(e->cap_stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+      t_ctx->capturing = true;
+      rc = body(e->cap_stream);
+      t_ctx->capturing = false;
+      if (cudaStreamEndCapture(e->cap_stream, &g) != cudaSuccess) rc = 1;
+    }
+    const int n = int(t_ctx->launches - l0);
+    t_ctx->launches = l0;
+    if (rc == 0 && g != nullptr && cudaGraphInstantiate(&ge.exec, g, 0) != cudaSuccess) { ge.exec = nullptr; rc = 1; }
+    if (g != nullptr) cudaGraphDestroy(g);
+    if (rc != 0) {                                     // capture is an optimisation: fall back to direct launches for good
+      cudaGetLastError();
+      e->graphs_enabled = false;
+      ge.exec = nullptr;
+      return body(st);
+    }
+    ge.launches = n;
+  }
+  SAMRS_CUDA_OK(cudaGraphLaunch(ge.exec, st));
+  t_ctx->launches += ge.launches;
+  return 0;
 }
 
 static void* g_attn_dbg = nullptr;            // device buffer for attention pipeline traces (tools only)
@@ -465,36 +519,36 @@ static int ln_rows(cudaStream_t st, const float* in, int ld_in, const float* g, 
 }
 
 template <int HD, int BX, int QBY, int KBY, int NKT>
-static int launch_attn2_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, const AttnParams& p, int num_sms, cudaStream_t st) {
+static int launch_attn2_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, const CUtensorMap& tT, const AttnParams& p, int num_sms, cudaStream_t st) {
   using C = Attn2Cfg<HD, BX, QBY, KBY, NKT>;
   SAMRS_TRY(opt_in_smem(attn_tc2_kernel<HD, BX, QBY, KBY, NKT>, C::kSmemBytes));
   const int units = p.num_qtiles * p.heads;
   const int grid = units < num_sms ? units : num_sms;
-  attn_tc2_kernel<HD, BX, QBY, KBY, NKT><<<grid, 384, C::kSmemBytes, st>>>(tQ, tKV, p);
+  attn_tc2_kernel<HD, BX, QBY, KBY, NKT><<<grid, 384, C::kSmemBytes, st>>>(tQ, tKV, tT, p);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
 }
 
-// encoder attention of one block: rel-pos terms + tcgen05 attention.  qkv: [4096][3D] fp16.
+// encoder attention of one block.  qkv: [4096][3D] fp16.  Windowed blocks form their rel-pos terms inside the attention
+// kernel (table in shared memory); global blocks first run the head-batched rel-pos GEMM whose output the kernel gathers.
 static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, const __half* reltab, bool global, __half* out) {
   const int D = e->D, hd = e->hd;
   if (hd != 64 && hd != 80) SAMRS_FAIL("head_dim must be 64 or 80");
-  {
+  const float scale_log2e = (1.0f / sqrtf(float(hd))) * 1.4426950408889634f;
+  if (global) {
     // decomposed rel-pos terms for every (head, token): G = q . [rel_pos_h ; rel_pos_w]^T as one head-batched
-    // tensor-core GEMM (A = the q columns of the qkv activation through a rank-3 tensor map)
+    // tensor-core GEMM (A = the q columns of the qkv activation through a rank-3 tensor map); the epilogue writes
+    // fp16(G / scale_log2e), the value the attention kernel feeds to its bias MMA
     ProfScope ps(PC_RELPOS, st);
-    const int NP = global ? 256 : 64;
+    const int NP = 256;
     CUtensorMap tA;
     SAMRS_TRY(make_tmap_3d(&tA, qkv, uint64_t(hd), uint64_t(e->heads), 4096, uint64_t(hd) * 2, uint64_t(3 * D) * 2, GEMM_BK, 1, GEMM_BM));
     GemmParams gp;
     gp.M = 4096; gp.N = NP; gp.K = hd; gp.out = e->rel; gp.ldc = NP; gp.bias = nullptr; gp.res = nullptr; gp.ldr = 0; gp.res_mod = 0;
-    gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.out_scale = 0.f; gp.dbg = nullptr; gp.dbg_mode = 0; gp.accumulate = 0;
-    // attention v2: the epilogue writes fp16(G / scale_log2e), the value the attention kernel feeds to its bias MMA, which
-    // halves the bytes written here and gathered there (global blocks: 67 -> 34 MB per layer)
-    const bool g16 = true;
-    gp.out_scale = 1.0f / ((1.0f / sqrtf(float(hd))) * 1.4426950408889634f);
-    SAMRS_TRY(launch_gemm_tc(nullptr, 8, reltab, hd, gp, g16, 0, e->num_sms, st, global ? 256 : 128, &tA));
+    gp.tiles_m = gp.tiles_n = 0; gp.batch = e->heads; gp.a_rank3 = 1; gp.out_batch_stride = (long long)4096 * NP; gp.dbg = nullptr; gp.dbg_mode = 0; gp.accumulate = 0;
+    gp.out_scale = 1.0f / scale_log2e;
+    SAMRS_TRY(launch_gemm_tc(nullptr, 8, reltab, hd, gp, true, 0, e->num_sms, st, 256, &tA));
   }
   ProfScope ps2(global ? PC_ATTN_GLOB : PC_ATTN_WIN, st);
   AttnParams p;
@@ -503,23 +557,26 @@ static int encoder_attention(Engine* e, cudaStream_t st, const __half* qkv, cons
   p.out = out;
   p.D = D;
   p.heads = e->heads;
-  p.scale_log2e = (1.0f / sqrtf(float(hd))) * 1.4426950408889634f;
+  p.scale_log2e = scale_log2e;
+  p.rel_scale = 1.0f / scale_log2e;
   p.dbg = static_cast<unsigned long long*>(g_attn_dbg);
   p.pv_split = 0;
-  CUtensorMap tQ, tKV;
+  CUtensorMap tQ, tKV, tT;
   const uint64_t pitch_x = uint64_t(3 * D) * 2, pitch_y = pitch_x * 64;
   if (global) {
     p.num_qtiles = 16;                                                // pairs of 128-query tiles
     SAMRS_TRY(make_tmap_3d(&tQ, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 64, 2));
     tKV = tQ;
-    if (hd == 64) return launch_attn2_inst<64, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
-    return launch_attn2_inst<80, 64, 2, 2, 32>(tQ, tKV, p, e->num_sms, st);
+    tT = tQ;                                                          // unused by the global variant
+    if (hd == 64) return launch_attn2_inst<64, 64, 2, 2, 32>(tQ, tKV, tT, p, e->num_sms, st);
+    return launch_attn2_inst<80, 64, 2, 2, 32>(tQ, tKV, tT, p, e->num_sms, st);
   }
   p.num_qtiles = 25;                                                  // windows (two 7-row halves each)
   SAMRS_TRY(make_tmap_3d(&tQ, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 14, 7));
   SAMRS_TRY(make_tmap_3d(&tKV, qkv, uint64_t(3 * D), 64, 64, pitch_x, pitch_y, 64, 14, 14));
-  if (hd == 64) return launch_attn2_inst<64, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
-  return launch_attn2_inst<80, 14, 7, 14, 1>(tQ, tKV, p, e->num_sms, st);
+  SAMRS_TRY(make_tmap_2d(&tT, reltab, uint64_t(hd), 64, uint64_t(hd) * 2, 64, 64));   // [27 + 27 + 10 zero rows][hd]
+  if (hd == 64) return launch_attn2_inst<64, 14, 7, 14, 1>(tQ, tKV, tT, p, e->num_sms, st);
+  return launch_attn2_inst<80, 14, 7, 14, 1>(tQ, tKV, tT, p, e->num_sms, st);
 }
 
 // ------------------------------------------------------------------ weight ingest
@@ -863,13 +920,9 @@ static int build_image_cache(Engine* e, cudaStream_t st) {
   return 0;
 }
 
-static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, float* features_out, cudaStream_t st) {
-  if (!e->weights_loaded) SAMRS_FAIL("encode: weights not loaded");
-  if (H < 1 || W < 1 || H > 1024 || W > 1024) SAMRS_FAIL("encode: image must be at most 1024x1024 (resize the long side to 1024 first)");
+// everything of an encode that only touches engine-owned memory: a_pe (patch operand) -> feat_tok + the per-image decoder cache
+static int encode_body(Engine* e, cudaStream_t st) {
   const int D = e->D, T = 4096;
-  preprocess_im2col_kernel<<<(4096 * 48 + 255) / 256, 256, 0, st>>>(img, H, W, chw, e->a_pe);
-  SAMRS_CUDA_OK(cudaGetLastError());
-  count_launch();
   // patch embedding + absolute position embedding (image_encoder.py:107-109)
   SAMRS_TRY(gemm_enc(e, st, e->a_pe, 768, e->w_patch, T, D, 768, e->x, D, false, e->b_patch, e->pos_embed, D, 0, 0));
   for (int i = 0; i < e->depth; ++i) {
@@ -894,11 +947,22 @@ static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, flo
   count_launch();
   SAMRS_TRY(gemm_enc(e, st, e->neck_col, 2304, e->w_neck2, T, 256, 2304, e->neck2, 256, false, nullptr, nullptr, 0, 0, 0));
   SAMRS_TRY((ln_rows<float, 0>(st, e->neck2, 256, e->neck3w, e->neck3b, 1e-6f, e->feat_tok, 256, T, 256)));
-  float* nchw = features_out ? features_out : e->feat_nchw;
+  return build_image_cache(e, st);
+}
+
+static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, float* features_out, cudaStream_t st) {
+  if (!e->weights_loaded) SAMRS_FAIL("encode: weights not loaded");
+  if (H < 1 || W < 1 || H > 1024 || W > 1024) SAMRS_FAIL("encode: image must be at most 1024x1024 (resize the long side to 1024 first)");
+  preprocess_im2col_kernel<<<(4096 * 48 + 255) / 256, 256, 0, st>>>(img, H, W, chw, e->a_pe);   // reads the caller's image
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  SAMRS_TRY(run_graphed(e, e->enc_graph, st, [&](cudaStream_t s) { return encode_body(e, s); }));
+  e->image_set = true;
+  float* nchw = features_out ? features_out : e->feat_nchw;                                      // writes the caller's buffer
   transpose_tok_to_nchw_kernel<<<dim3(128, 8), dim3(32, 8), 0, st>>>(e->feat_tok, nchw, 256);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
-  return build_image_cache(e, st);
+  return 0;
 }
 
 // ------------------------------------------------------------------ decoder
@@ -933,14 +997,18 @@ static int token_attention(Engine* e, cudaStream_t st, const DecAttn& a, const f
   return sgemm(st, e->d_tmp256d, 256, a.wo, 256, out256, 256, a.bo, residual, 256, 0, BT, 256, 256, 0);
 }
 
+static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, int multimask);
+
 static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const float* points, const int* labels, int NP,
                         const float* mask_in, int B, int multimask, float* lowres_out, float* iou_out) {
   const int pad = (points && !boxes) ? 1 : 0;
   const int Ns = (points ? NP + pad : 0) + (boxes ? 2 : 0);
-  const int T = 5 + Ns, BT = B * T;
+  const int T = 5 + Ns;
   if (T > 16) SAMRS_FAIL("decode: at most 11 sparse prompt tokens per prompt are supported");
   SAMRS_TRY(ensure_decoder_scratch(e, B));
+  if (mask_in) SAMRS_TRY(ensure_mask_scratch(e, B));
   SAMRS_TRY(opt_in_smem(tok_self_attn_kernel, 64 * 1024));
+  // (1) kernels that read the caller's prompt buffers: tokens, and the per-prompt dense embedding of mask prompts
   PromptParams pp;
   pp.gauss = e->gauss; pp.point_emb = e->point_emb; pp.not_a_point = e->not_a_point;
   pp.iou_token = e->iou_token; pp.mask_tokens = e->mask_tokens;
@@ -949,18 +1017,35 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
   prompt_tokens_kernel<<<B, 128, 0, st>>>(pp);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
-
-  // image-side layer-0 operands: shared across prompts unless a mask prompt makes src per-prompt
-  const float *K0 = e->K0, *V0 = e->V0, *Qi0 = e->Qi0, *src = e->src0;
-  size_t kv_stride = 0;
-  int src_mod = 4096;
   if (mask_in) {
-    SAMRS_TRY(ensure_mask_scratch(e, B));
     MaskEmbedParams mp{mask_in, e->md_w0, e->md_b0, e->md_g1, e->md_be1, e->md_w3, e->md_b3, e->md_g4, e->md_be4, e->md_w6, e->md_b6,
                        e->feat_tok, e->d_src};
     mask_embed_src_kernel<<<(B * 4096 + 127) / 128, 128, 0, st>>>(mp, B);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
+  }
+  // (2) the two-way transformer, hyper-network / IoU heads and the first upscaling stage: engine-owned memory only, one graph
+  //     per (prompts, tokens per prompt, multimask, mask prompt)
+  const uint64_t key = uint64_t(B) | (uint64_t(T) << 16) | (uint64_t(multimask ? 1 : 0) << 24) | (uint64_t(mask_in ? 1 : 0) << 25);
+  SAMRS_TRY(run_graphed(e, e->dec_graphs[key], st, [&](cudaStream_t s) { return decode_body(e, s, mask_in != nullptr, B, T, multimask); }));
+  // (3) kernels that write the caller's outputs: IoU predictions and the fused ConvT2 + GELU + hyper-network product
+  const int NM = multimask ? 3 : 1;
+  SAMRS_CUDA_OK(cudaMemcpyAsync(iou_out, e->d_iou_all, size_t(B) * NM * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  const unsigned ublocks = unsigned((size_t(B) * 16384 + 127) / 128);
+  if (NM == 1) upscale2_hyper_kernel<1><<<ublocks, 128, 0, st>>>(e->d_P + 256, 512, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
+  else upscale2_hyper_kernel<3><<<ublocks, 128, 0, st>>>(e->d_P + 256, 512, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, int multimask) {
+  const int BT = B * T;
+  // image-side layer-0 operands: shared across prompts unless a mask prompt makes src per-prompt
+  const float *K0 = e->K0, *V0 = e->V0, *Qi0 = e->Qi0, *src = e->src0;
+  size_t kv_stride = 0;
+  int src_mod = 4096;
+  if (has_mask) {
     const DecLayer& L0 = e->dl[0];
     SAMRS_TRY(sgemm(st, e->d_src, 256, L0.t2i.wk, 256, e->d_Kp, 128, L0.t2i.bk, e->pek[0], 128, 4096, B * 4096, 128, 256, 0));
     SAMRS_TRY(sgemm(st, e->d_src, 256, L0.t2i.wv, 256, e->d_Vp, 128, L0.t2i.bv, nullptr, 0, 0, B * 4096, 128, 256, 0));
@@ -1054,15 +1139,10 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
   SAMRS_TRY(sgemm(st, e->d_hy_t, 256, e->iou_head.w[0], 256, e->d_hy_a, 256, e->iou_head.b[0], nullptr, 0, 0, B, 256, 256, 1));
   SAMRS_TRY(sgemm(st, e->d_hy_a, 256, e->iou_head.w[1], 256, e->d_hy_b, 256, e->iou_head.b[1], nullptr, 0, 0, B, 256, 256, 1));
   // last layer restricted to the returned slice: rows m_first .. m_first+NM-1 of the (4,256) weight
-  SAMRS_TRY(sgemm(st, e->d_hy_b, 256, e->iou_head.w[2] + m_first * 256, 256, iou_out, NM, e->iou_head.b[2] + m_first, nullptr, 0, 0, B, NM,
+  SAMRS_TRY(sgemm(st, e->d_hy_b, 256, e->iou_head.w[2] + m_first * 256, 256, e->d_iou_all, NM, e->iou_head.b[2] + m_first, nullptr, 0, 0, B, NM,
                   256, 0));
-  // upscaling: ConvT1 columns of P2 -> LN2d+GELU per 64-channel group (in place) -> fused ConvT2+GELU+hyper product
+  // upscaling: ConvT1 columns of P2 -> LN2d+GELU per 64-channel group (in place); ConvT2+GELU+hyper product follows outside
   ln64_gelu_grouped_kernel<<<unsigned((size_t(M4) * 4 * 16 + 255) / 256), 256, 0, st>>>(e->d_P, 512, 256, e->up_lnw, e->up_lnb, M4);
-  SAMRS_CUDA_OK(cudaGetLastError());
-  count_launch();
-  const unsigned ublocks = unsigned((size_t(B) * 16384 + 127) / 128);
-  if (NM == 1) upscale2_hyper_kernel<1><<<ublocks, 128, 0, st>>>(e->d_P + 256, 512, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
-  else upscale2_hyper_kernel<3><<<ublocks, 128, 0, st>>>(e->d_P + 256, 512, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -1104,7 +1184,7 @@ int samrs_create(int device, int embed_dim, int depth, int num_heads, const int*
   e->D = embed_dim; e->depth = depth; e->heads = num_heads; e->hd = hd;
   e->global_idx.assign(global_idx, global_idx + n_global);
   e->num_sms = prop.multiProcessorCount;
-  if (alloc_activations(e) != 0) {
+  if (alloc_activations(e) != 0 || cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
     samrs_destroy(e);
     return 1;
   }
@@ -1401,6 +1481,15 @@ int samrs_profile(void* engine, int enable, float* ms_by_category, int* launches
   return 0;
 }
 
+int samrs_set_graphs(void* engine, int enable) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  e->graphs_enabled = enable != 0;
+  if (!enable) { cudaDeviceSynchronize(); e->drop_graphs(); }
+  return 0;
+}
+
 int samrs_launch_count(void* engine, int64_t* out) {
   Engine* e = static_cast<Engine*>(engine);
   if (!e || !out) return 1;
@@ -1418,6 +1507,9 @@ void samrs_destroy(void* engine) {
   Engine* e = static_cast<Engine*>(engine);
   if (!e) return;
   cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  e->drop_graphs();
+  if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
   for (void* p : e->allocs) cudaFree(p);
   for (void* p : e->weight_allocs) cudaFree(p);
   for (auto& r : e->ctx.prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

@@ -32,6 +32,7 @@ ABI = {
     "samrs_resize_bilinear_u8": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),
     "samrs_rle_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, ctypes.c_longlong, _vp, _vp, _vp]),
     "samrs_profile": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _i]),
+    "samrs_set_graphs": (_i, [_vp, _i]),
     "samrs_launch_count": (_i, [_vp, _i64p]),
     "samrs_last_error": (ctypes.c_char_p, [_vp]),
     "samrs_destroy": (None, [_vp]),
@@ -271,6 +272,10 @@ class Engine:
         ms, cnt = (ctypes.c_float * n)(), (ctypes.c_int * n)()
         self._check(self._lib.samrs_profile(self._h, 0, ms, cnt, n), "profile")
         return {k: (float(ms[i]), int(cnt[i])) for i, k in enumerate(self.PROFILE_CATEGORIES)}
+
+    def set_graphs(self, enable: bool) -> None:
+        """CUDA-graph replay of the encode / decode bodies (default on); off = every kernel is launched directly."""
+        self._check(self._lib.samrs_set_graphs(self._h, int(bool(enable))), "set_graphs")
 
     def launch_count(self) -> int:
         c = ctypes.c_int64(0)

@@ -77,12 +77,13 @@ def _decode_chunks(predictor, engine, boxes_dev: torch.Tensor, original_hw, chun
 
 
 def tile_outputs(predictor, engine, image: np.ndarray, boxes: torch.Tensor, labels: torch.Tensor, canvas: torch.Tensor,
-                 chunk: int = 20, instance: bool = True, capacity_per_mask: int = 65536):
+                 chunk: int = 20, instance: bool = True, capacity_per_mask: int = 1 << 17):
     """Both products of one iteration of the driver's per-image loop (`main_sam_hbox_semantic.py:155-204`) from ONE
     encode: the label map (painter reduce) in `canvas` and, if `instance`, the run-length payload of every mask.
 
     Everything is enqueued on the current stream; nothing is copied to the host.  Returns `(canvas, payload)` with
-    `payload = [(counts, offsets, area, n_masks, capacity), ...]` per chunk (CUDA tensors).  1024 x 1024 tiles use the
+    `payload = [(counts, offsets, area, n_masks, capacity, source), ...]` per chunk (CUDA tensors; `source` = what was
+    encoded, kept so that `fetch_runs` can encode again should the runs not fit).  1024 x 1024 tiles use the
     fused kernels (upsample + threshold + paint / + RLE straight from the 256 x 256 logits); other sizes go through the
     general postprocess and paint / encode the bool masks."""
     predictor.set_image(image)
@@ -98,13 +99,13 @@ def tile_outputs(predictor, engine, image: np.ndarray, boxes: torch.Tensor, labe
             engine.semantic_reduce(low, ldev[s:s + n], canvas)
             if instance:
                 cap = n * capacity_per_mask
-                payload.append(engine.rle_encode(low_res=low, capacity=cap) + (n, cap))
+                payload.append(engine.rle_encode(low_res=low, capacity=cap) + (n, cap, ("low_res", low)))
         else:
             masks = engine.postprocess(low, predictor.input_size, (H, W))
             engine.paint_masks(masks, ldev[s:s + n], canvas)
             if instance:
                 cap = n * capacity_per_mask
-                payload.append(engine.rle_encode(masks=masks, capacity=cap) + (n, cap))
+                payload.append(engine.rle_encode(masks=masks, capacity=cap) + (n, cap, ("masks", masks)))
     return canvas, payload
 
 
@@ -125,13 +126,27 @@ def instance_tile(predictor, engine, image: np.ndarray, boxes: torch.Tensor, lab
     return _records_from_payload(engine, payload, H, W, boxes.detach().cpu().numpy(), [int(v) for v in labels], categories, None)
 
 
-def _records_from_payload(engine, payload, H, W, boxes_np, labels, categories, rboxes_np, low_keep=None):
+def fetch_runs(engine, entry, reencode: bool = True):
+    """Host copies `(counts[:total], offsets, area)` of one payload entry.  Only the runs that exist are copied (the host
+    learns their number from `offsets[-1]`); if they did not fit the capacity the chunk is encoded again with the exact
+    size (noise-like masks - e.g. from the synthetic checkpoint - can have 100k+ runs each)."""
+    counts, offsets, area, n, cap, (kind, src) = entry
+    off = offsets.cpu()
+    total = int(off[-1])
+    if total > cap:
+        if not reencode:                                  # a second thread must not drive the engine: the caller sizes the buffer
+            raise RuntimeError(f"rle: {total} runs exceed the capacity of {cap} for {n} masks; raise capacity_per_mask")
+        counts, offsets, area = engine.rle_encode(capacity=total, **{kind: src})
+        off = offsets.cpu()
+    return counts[:total].cpu(), off, area.cpu()
+
+
+def _records_from_payload(engine, payload, H, W, boxes_np, labels, categories, rboxes_np, reencode: bool = True):
     from . import rle as host_rle
     records, s = [], 0
-    for (counts, offsets, area, n, cap) in payload:
-        total = int(offsets[-1])                         # synchronises: the host needs the payload anyway
-        if total > cap:
-            raise RuntimeError(f"rle: {total} runs exceed the capacity of {cap}; raise capacity_per_mask")
+    for entry in payload:
+        n = entry[3]
+        counts, offsets, area = fetch_runs(engine, entry, reencode)
         records += host_rle.instance_records(counts, offsets, area, H, W, boxes_np[s:s + n], labels[s:s + n], categories,
                                              rboxes=None if rboxes_np is None else rboxes_np[s:s + n])
         s += n
@@ -150,7 +165,8 @@ class TileJob:
 
 
 def run(predictor, jobs: Iterable, save_dir: str = None, mapping=None, categories: Sequence[str] = None, chunk: int = 20,
-        instance: bool = True, writer_threads: int = 4, loader_threads: int = 2, depth: int = 4, on_tile=None) -> Dict[str, float]:
+        instance: bool = True, writer_threads: int = 4, loader_threads: int = 2, depth: int = 4, on_tile=None,
+        capacity_per_mask: int = 1 << 19) -> Dict[str, float]:
     """The per-rank loop that replaces `main_sam_hbox_semantic.py:110-216` (and the rhbox variant when jobs carry rboxes).
 
       loader threads  materialise each job's image into a pinned ring slot (JPEG / PNG decode off the GPU thread)
@@ -174,6 +190,7 @@ def run(predictor, jobs: Iterable, save_dir: str = None, mapping=None, categorie
     done_q: "queue.Queue" = queue.Queue()
     errors: List[BaseException] = []
     lock = threading.Lock()
+    side = torch.cuda.Stream(device=device)                    # the finisher's copies
 
     class Slot:
         def __init__(self):
@@ -217,17 +234,10 @@ def run(predictor, jobs: Iterable, save_dir: str = None, mapping=None, categorie
                 label_map = slot.canvas_h[: H * W].view(H, W).numpy().copy()
                 records = []
                 if instance:
-                    from . import rle as host_rle
-                    s = 0
-                    boxes_np = np.asarray(job.boxes)
                     rb = None if job.rboxes is None else np.asarray(job.rboxes)
-                    for (counts, offsets, area, n, cap) in payload_h:
-                        if int(offsets[-1]) > cap:
-                            raise RuntimeError(f"rle: {int(offsets[-1])} runs exceed the capacity of {cap}")
-                        records += host_rle.instance_records(counts, offsets, area, H, W, boxes_np[s:s + n],
-                                                             [int(v) for v in job.labels[s:s + n]], categories,
-                                                             rboxes=None if rb is None else rb[s:s + n])
-                        s += n
+                    with torch.cuda.stream(side):              # D2H of the runs that exist, off the GPU thread's stream
+                        records = _records_from_payload(engine, payload_h, H, W, np.asarray(job.boxes),
+                                                        [int(v) for v in job.labels], categories, rb, reencode=False)
                 free_slots.put(slot)                           # pinned buffers are copied out: recycle the slot
                 if on_tile is not None:
                     on_tile(job, label_map, records)
@@ -262,15 +272,10 @@ def run(predictor, jobs: Iterable, save_dir: str = None, mapping=None, categorie
             canvas = slot.canvas_d[: H * W].view(H, W)
             boxes = torch.as_tensor(np.asarray(job.boxes))
             labels = torch.as_tensor(np.asarray(job.labels))
-            _, payload = tile_outputs(predictor, engine, view.numpy(), boxes, labels, canvas, chunk, instance)
+            _, payload = tile_outputs(predictor, engine, view.numpy(), boxes, labels, canvas, chunk, instance, capacity_per_mask)
             slot.canvas_h[: H * W].copy_(canvas.view(-1), non_blocking=True)
-            payload_h = []
-            for (counts, offsets, area, n, cap) in payload:
-                # only offsets[-1] runs are meaningful, but the host learns that number with the copy: ship a bounded slab
-                payload_h.append((counts.to("cpu", non_blocking=True), offsets.to("cpu", non_blocking=True),
-                                  area.to("cpu", non_blocking=True), n, cap))
             slot.event.record(torch.cuda.current_stream(device))
-            done_q.put((job, slot, H, W, payload_h))
+            done_q.put((job, slot, H, W, payload))            # the finisher copies the runs once it knows how many there are
             tiles += 1
             masks += int(boxes.shape[0])
     finally:
