@@ -273,6 +273,10 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   if (mcast) SAMRS_FAIL("gemm: the TMA-multicast variant exists only in -DSAMRS_EXPERIMENTS builds");
 #endif
   const int grid = tiles < num_sms ? tiles : num_sms;
+  if (act == 3) {
+    if (bn != 128 || out_half || p.hyper == nullptr || p.low == nullptr) SAMRS_FAIL("gemm: the up-scaling epilogue needs a 128-wide fp32 tile and its operands");
+    return launch_gemm_inst<128, false, 3>(tA, tB, tC, p, grid, stream);
+  }
 #define SAMRS_GEMM_CASE(BN_)                                                                        \
   if (bn == BN_) {                                                                                  \
     if (out_half && act == 0) return launch_gemm_inst<BN_, true, 0>(tA, tB, tC, p, grid, stream);       \
@@ -360,7 +364,8 @@ struct Engine {
   float *up_w1r, *up_b1r, *up_lnw, *up_lnb, *up_w2r, *up_b2;
   Mlp3 hyper[4], iou_head;
   // split-fp16 ([hi|hi|lo] x 256) weights of the four tensor-core decoder GEMMs and their epilogue operands
-  __half *wd_p1 = nullptr, *wd_p2 = nullptr, *wd_o0 = nullptr, *wd_o1 = nullptr;
+  __half *wd_p1 = nullptr, *wd_p2 = nullptr, *wd_o0 = nullptr, *wd_o1 = nullptr, *wd_up2 = nullptr;
+  float* up_b2r = nullptr;             // ConvT2 bias tiled over the four output sub-positions [4][32]
   float *bias_p1 = nullptr, *bias_p2 = nullptr, *R1 = nullptr, *R2 = nullptr;
   float* dense_pe = nullptr;           // [4096][256]
   float* pek[5] = {nullptr};           // dense_pe * W^T for: l0.t2i.k, l0.i2t.q, l1.t2i.k, l1.i2t.q, final.k  [4096][128]
@@ -387,7 +392,7 @@ struct Engine {
   float *d_tok0 = nullptr, *d_q = nullptr, *d_tmp256a = nullptr, *d_tmp256b = nullptr, *d_tmp256c = nullptr, *d_tmp256d = nullptr;
   float *d_tmp128a = nullptr, *d_tmp128b = nullptr, *d_tmp128c = nullptr, *d_mlp = nullptr;
   float *d_keys = nullptr, *d_P = nullptr, *d_hyper = nullptr, *d_hy_t = nullptr, *d_hy_a = nullptr, *d_hy_b = nullptr, *d_iou_all = nullptr, *d_low = nullptr;
-  __half *d_keysA = nullptr, *d_ioA = nullptr;
+  __half *d_keysA = nullptr, *d_ioA = nullptr, *d_up1 = nullptr;   // d_up1: split-fp16 GELU(LN(ConvT1)) [cap*16384][192]
   int mask_cap = 0;                    // mask-prompt path scratch (per-prompt layer-0 operands), allocated on first use
   float *d_Kp = nullptr, *d_Vp = nullptr, *d_Qp = nullptr, *d_src = nullptr;
 
@@ -798,6 +803,8 @@ static int load_weights_impl(Engine* e, const SrcMap& m, cudaStream_t st) {
   SAMRS_TRY(e->alloc(&e->wd_p2, size_t(512) * 768));
   SAMRS_TRY(e->alloc(&e->wd_o0, size_t(256) * 384));
   SAMRS_TRY(e->alloc(&e->wd_o1, size_t(256) * 384));
+  SAMRS_TRY(e->alloc(&e->wd_up2, size_t(128) * 192));
+  SAMRS_TRY(e->alloc(&e->up_b2r, 128));
   split_into(e->dl[1].t2i.wk, 128, 256, e->wd_p1);
   split_into(e->dl[1].t2i.wv, 128, 256, e->wd_p1 + size_t(128) * 768);
   split_into(e->dl[1].i2t.wq, 128, 256, e->wd_p1 + size_t(256) * 768);
@@ -806,6 +813,8 @@ static int load_weights_impl(Engine* e, const SrcMap& m, cudaStream_t st) {
   split_into(e->up_w1r, 256, 256, e->wd_p2 + size_t(256) * 768);
   split_into(e->dl[0].i2t.wo, 256, 128, e->wd_o0);
   split_into(e->dl[1].i2t.wo, 256, 128, e->wd_o1);
+  split_into(e->up_w2r, 128, 64, e->wd_up2);                 // ConvT2 as a GEMM: N = 4 sub-positions x 32 channels, K = 64
+  tile_bias_kernel<<<1, 128, 0, st>>>(e->up_b2, e->up_b2r, 32, 4);
   SAMRS_TRY(e->alloc(&e->bias_p1, 384));
   SAMRS_TRY(e->alloc(&e->bias_p2, 512));
   SAMRS_CUDA_OK(cudaMemcpyAsync(e->bias_p1, e->dl[1].t2i.bk, 512, cudaMemcpyDeviceToDevice, st));
@@ -871,6 +880,7 @@ static int ensure_decoder_scratch(Engine* e, int B) {
   e->release(&e->d_P); SAMRS_TRY(e->alloc(&e->d_P, c * 4096 * 512));
   e->release(&e->d_keysA); SAMRS_TRY(e->alloc(&e->d_keysA, c * 4096 * 768));
   e->release(&e->d_ioA); SAMRS_TRY(e->alloc(&e->d_ioA, c * 4096 * 384));
+  e->release(&e->d_up1); SAMRS_TRY(e->alloc(&e->d_up1, c * 16384 * 192));
   e->release(&e->d_hyper); SAMRS_TRY(e->alloc(&e->d_hyper, c * 4 * 32));
   e->release(&e->d_hy_t); SAMRS_TRY(e->alloc(&e->d_hy_t, c * 256));
   e->release(&e->d_hy_a); SAMRS_TRY(e->alloc(&e->d_hy_a, c * 256));
@@ -1031,11 +1041,15 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
   // (3) kernels that write the caller's outputs: IoU predictions and the fused ConvT2 + GELU + hyper-network product
   const int NM = multimask ? 3 : 1;
   SAMRS_CUDA_OK(cudaMemcpyAsync(iou_out, e->d_iou_all, size_t(B) * NM * sizeof(float), cudaMemcpyDeviceToDevice, st));
-  const unsigned ublocks = unsigned((size_t(B) * 16384 + 127) / 128);
-  if (NM == 1) upscale2_hyper_kernel<1><<<ublocks, 128, 0, st>>>(e->d_P + 256, 512, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
-  else upscale2_hyper_kernel<3><<<ublocks, 128, 0, st>>>(e->d_P + 256, 512, e->up_w2r, e->up_b2, e->d_hyper, lowres_out, B);
-  SAMRS_CUDA_OK(cudaGetLastError());
-  count_launch();
+  {
+    // ConvT2 on the tensor cores (3-term split fp16, K' = 192) with GELU and the hyper-network product in the epilogue
+    GemmParams p;
+    p.M = B * 16384; p.N = 128; p.K = 192; p.out = e->d_P; p.ldc = 512; p.bias = e->up_b2r; p.res = nullptr; p.ldr = 0; p.res_mod = 0;
+    p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f; p.dbg = nullptr; p.dbg_mode = 0;
+    p.accumulate = 0;
+    p.hyper = e->d_hyper; p.low = lowres_out; p.hyper_nm = NM;
+    SAMRS_TRY(launch_gemm_tc(e->d_up1, 192, e->wd_up2, 192, p, false, 3, e->num_sms, st, 128));
+  }
   return 0;
 }
 
@@ -1142,7 +1156,7 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
   SAMRS_TRY(sgemm(st, e->d_hy_b, 256, e->iou_head.w[2] + m_first * 256, 256, e->d_iou_all, NM, e->iou_head.b[2] + m_first, nullptr, 0, 0, B, NM,
                   256, 0));
   // upscaling: ConvT1 columns of P2 -> LN2d+GELU per 64-channel group (in place); ConvT2+GELU+hyper product follows outside
-  ln64_gelu_grouped_kernel<<<unsigned((size_t(M4) * 4 * 16 + 255) / 256), 256, 0, st>>>(e->d_P, 512, 256, e->up_lnw, e->up_lnb, M4);
+  ln64_gelu_split_kernel<<<unsigned((size_t(M4) * 4 * 16 + 255) / 256), 256, 0, st>>>(e->d_P, 512, 256, e->up_lnw, e->up_lnb, M4, e->d_up1);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;

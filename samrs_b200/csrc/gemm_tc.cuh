@@ -32,6 +32,10 @@ struct GemmParams {
   unsigned long long* dbg;   // optional: CTA 0 records clock64() at pipeline events (tools/gemm_trace.py)
   int accumulate;       // fp32 output only: out += result (TMA reduce-add) instead of out = result
   int dbg_mode;         // tools only (results are garbage): bit0 skip TMA loads, bit1 skip MMAs, bit2 skip the epilogue
+  // ACT == 3 (mask decoder, second up-scaling stage fused with the hyper-network product; see gemm_epilogue_warp_upscale2):
+  const float* hyper = nullptr;   // [B][hyper_nm][32]
+  float* low = nullptr;           // [B][hyper_nm][256][256] low-res mask logits
+  int hyper_nm = 0;
 };
 // Pipeline traces and the "remove one stage" experiments of tools/gemm_trace.py exist only in builds with
 // -DSAMRS_EXPERIMENTS (build.sh exp -> libsamrs_b200_exp.so); the product library compiles them away.
@@ -137,6 +141,45 @@ __device__ __forceinline__ void gemm_epilogue_warp_half(const GemmParams& p, con
   }
 }
 
+// ACT == 3: the GEMM is ConvTranspose2d(64 -> 32, k2 s2) of the mask decoder's up-scaling (mask_decoder.py:58) over rows
+// m = ((b * 4096 + token) * 4 + d1) (one 128 x 128 position each, 64 input channels) and columns n = d2 * 32 + c (the four
+// output sub-positions x 32 channels).  The epilogue finishes the reference's chain in registers: + bias -> GELU (:59) ->
+// mask[b, m', y, x] = sum_c hyper[b, m', c] * upscaled[b, c, y, x] (:163-167), so the (B, 32, 256, 256) tensor is never
+// materialised: each 32-column chunk is one output pixel of the row's 2 x 2 block, written as one float per mask.
+template <int BN>
+__device__ __forceinline__ void gemm_epilogue_warp_upscale2(const GemmParams& p, uint32_t t_addr, int row0, float oscale, int lane,
+                                                            const float (&bias_r)[BN / 32], int chunk_begin, int chunk_end) {
+  static_assert(BN == 128, "the up-scaling epilogue expects the four 32-channel groups in one tile");
+  const int m = row0 + lane;
+  const bool ok = m < p.M;
+  const int mm = ok ? m : 0;
+  const int b = mm >> 14, rem = mm & 16383, token = rem >> 2, d1 = rem & 3;
+  const int Y = 2 * (token >> 6) + (d1 >> 1), X = 2 * (token & 63) + (d1 & 1);      // position in the 128 x 128 grid
+  const int bw = __shfl_sync(0xffffffffu, b, 0);                                   // 16384 rows per prompt: uniform in a tile
+#pragma unroll
+  for (int c = 0; c < BN / 32; ++c) {
+    if (c < chunk_begin || c >= chunk_end) continue;
+    uint32_t v[32];
+    tmem_ld32(t_addr + uint32_t(c * 32), v);
+    tc_wait_ld();
+    float f[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] = gelu_erf(fmaf(__uint_as_float(v[j]), oscale, __shfl_sync(0xffffffffu, bias_r[c], j)));
+    const int y = 2 * Y + (c >> 1), x = 2 * X + (c & 1);
+    for (int mk = 0; mk < p.hyper_nm; ++mk) {
+      const float4* hy = reinterpret_cast<const float4*>(p.hyper + (size_t(bw) * p.hyper_nm + mk) * 32);
+      float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; j += 2) {
+        const float4 h0 = __ldg(hy + j), h1 = __ldg(hy + j + 1);
+        o0 = fmaf(h0.x, f[4 * j], o0); o0 = fmaf(h0.y, f[4 * j + 1], o0); o0 = fmaf(h0.z, f[4 * j + 2], o0); o0 = fmaf(h0.w, f[4 * j + 3], o0);
+        o1 = fmaf(h1.x, f[4 * j + 4], o1); o1 = fmaf(h1.y, f[4 * j + 5], o1); o1 = fmaf(h1.z, f[4 * j + 6], o1); o1 = fmaf(h1.w, f[4 * j + 7], o1);
+      }
+      if (ok) p.low[((size_t(b) * p.hyper_nm + mk) * 256 + y) * 256 + x] = o0 + o1;
+    }
+  }
+}
+
 // Epilogue of one accumulator tile, executed by one warp for its 32 TMEM lanes (rows row0 .. row0+31), 32 columns at
 // a time: tcgen05.ld -> scale + bias (+ residual) + activation in registers -> the warp's 32x32 block is staged in
 // shared memory and written out by ONE asynchronous TMA store (rows / columns beyond M / N are clipped by the TMA
@@ -151,6 +194,10 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
                                                    int lane, const float (&bias_r)[BN / 32], int chunk_begin, int chunk_end) {
   if constexpr (OUT_HALF) {
     gemm_epilogue_warp_half<BN, ACT>(p, tmC, t_addr, row0, n0, bt, oscale, stage, nstaged, lane, bias_r, chunk_begin, chunk_end);
+    return;
+  }
+  if constexpr (ACT == 3) {
+    gemm_epilogue_warp_upscale2<BN>(p, t_addr, row0, oscale, lane, bias_r, chunk_begin, chunk_end);
     return;
   }
   constexpr int NCH = BN / 32;
