@@ -84,6 +84,13 @@ int samrs_resize_bilinear_u8(void* engine, const uint8_t* src_hwc, int H, int W,
 int samrs_rle_encode(void* engine, const uint8_t* masks, const float* lowres, int B, int H, int W,
                      uint32_t* counts_out, long long capacity, long long* offsets_out, long long* area_out, void* stream);
 
+/* compressed COCO string of runs produced by samrs_rle_encode (the `counts` string maskUtils.encode returns,
+ * main_sam_hbox_semantic.py:200-201; scheme of pycocotools' rleToString, which is neither vendored nor installed: parity
+ * unpinned, host restatement in samrs_b200/rle.py).  Mask b's characters are chars_out[char_offsets_out[b] .. [b+1]);
+ * if char_offsets_out[B] > char_capacity the tail was not written. */
+int samrs_rle_string(void* engine, const uint32_t* counts, const long long* offsets /*[B+1]*/, int B, long long run_capacity,
+                     uint8_t* chars_out, long long char_capacity, long long* char_offsets_out /*[B+1]*/, void* stream);
+
 /* device-side timing by kernel category (bench.py's roofline): enable=1 starts recording CUDA events around the
  * engine's launches on their stream; enable=0 synchronises and returns milliseconds / scope counts per category:
  * 0 tcgen05 GEMM, 1 windowed attention, 2 global attention, 3 rel-pos terms, 4 LayerNorm, 5 whole encode,

@@ -1443,6 +1443,31 @@ int samrs_rle_encode(void* engine, const uint8_t* masks, const float* lowres, in
   return 0;
 }
 
+int samrs_rle_string(void* engine, const uint32_t* counts, const long long* offsets, int B, long long run_capacity,
+                     uint8_t* chars_out, long long char_capacity, long long* char_offsets_out, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B < 0 || !offsets || !char_offsets_out || (B > 0 && !counts) || (!chars_out && char_capacity > 0))
+    return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_string: bad arguments"));
+  ProfScope ps(PC_EPILOGUE, st);
+  if (B + 1 > e->rle_runs_cap) {
+    e->release(&e->rle_runs);
+    e->release(&e->rle_tstate);
+    if (e->alloc(&e->rle_runs, size_t(B) + 1) != 0) return set_err(e, 1);
+    if (e->alloc(&e->rle_tstate, (size_t(B) + 1) * RLE_THREADS * 2) != 0) return set_err(e, 1);
+    e->rle_runs_cap = B + 1;
+  }
+  if (B > 0) coco_string_kernel<false><<<B, RLE_THREADS, 0, st>>>(counts, offsets, run_capacity, e->rle_runs, nullptr, nullptr, 0);
+  rle_offsets_kernel<<<1, 32, 0, st>>>(e->rle_runs, B, char_offsets_out);
+  if (B > 0) coco_string_kernel<true><<<B, RLE_THREADS, 0, st>>>(counts, offsets, run_capacity, nullptr, char_offsets_out, chars_out, char_capacity);
+  count_launch(B > 0 ? 3 : 1);
+  if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "rle_string launch failed"));
+  return 0;
+}
+
 int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_ids, int B, uint8_t* label_map, int H, int W, void* stream) {
   Engine* e = static_cast<Engine*>(engine);
   if (!e) return 1;

@@ -174,6 +174,79 @@ __global__ void __launch_bounds__(RLE_THREADS) rle_scan_kernel(const uint32_t* _
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Compressed COCO string of the runs (what `maskUtils.encode` returns in rle["counts"], main_sam_hbox_semantic.py:200-201):
+// every run - from the fourth on, its difference to the run two before - is written as 5-bit groups, least significant
+// first, bit 5 = "more groups follow", bit 4 of the last group = sign, each group + 48 as one ASCII character
+// (pycocotools rleToString; parity with that un-vendored library is unpinned, the host restatement is samrs_b200/rle.py).
+// One CTA per mask, 1024 runs per step: a block-wide exclusive scan of the group counts gives every run its position.
+// EMIT == false: nchars[b] only.  EMIT == true: the characters at char_offsets[b].
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int coco_groups(long long x) {
+  int n = 0;
+  bool more = true;
+  while (more) {
+    const int c = int(x & 0x1f);
+    x >>= 5;
+    more = (c & 0x10) ? (x != -1) : (x != 0);
+    ++n;
+  }
+  return n;
+}
+
+template <bool EMIT>
+__global__ void __launch_bounds__(RLE_THREADS) coco_string_kernel(const uint32_t* __restrict__ counts, const long long* __restrict__ offsets,
+                                                                  long long run_capacity, long long* __restrict__ nchars,
+                                                                  const long long* __restrict__ char_offsets, uint8_t* __restrict__ chars,
+                                                                  long long char_capacity) {
+  const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+  const long long base = offsets[b];
+  long long n = offsets[b + 1] - base;
+  if (base + n > run_capacity) n = 0;                              // the runs themselves did not fit: nothing to encode
+  const uint32_t* c = counts + base;
+  __shared__ int s_warp[RLE_THREADS / 32];
+  long long running = 0;
+  const long long out0 = EMIT ? char_offsets[b] : 0;
+  for (long long i0 = 0; i0 < n; i0 += RLE_THREADS) {
+    const long long i = i0 + t;
+    long long x = 0;
+    int k = 0;
+    if (i < n) {
+      x = (long long)c[i];
+      if (i > 2) x -= (long long)c[i - 2];
+      k = coco_groups(x);
+    }
+    int inc = k;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, inc, o);
+      if (lane >= o) inc += u;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int w = 0; w < RLE_THREADS / 32; ++w) {
+      if (w < warp) wbase += s_warp[w];
+      total += s_warp[w];
+    }
+    if (EMIT && i < n) {
+      long long p = out0 + running + wbase + inc - k;
+      bool more = true;
+      while (more) {
+        int ch = int(x & 0x1f);
+        x >>= 5;
+        more = (ch & 0x10) ? (x != -1) : (x != 0);
+        if (more) ch |= 0x20;
+        if (p < char_capacity) chars[p] = uint8_t(ch + 48);
+        ++p;
+      }
+    }
+    running += total;
+    __syncthreads();
+  }
+  if (!EMIT && t == 0) nchars[b] = running;
+}
+
 __global__ void rle_offsets_kernel(const long long* __restrict__ runs, int B, long long* __restrict__ offsets) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     long long acc = 0;

@@ -31,6 +31,7 @@ ABI = {
     "samrs_paint_masks": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "samrs_resize_bilinear_u8": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),
     "samrs_rle_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, ctypes.c_longlong, _vp, _vp, _vp]),
+    "samrs_rle_string": (_i, [_vp, _vp, _vp, _i, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp, _vp]),
     "samrs_profile": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _i]),
     "samrs_set_graphs": (_i, [_vp, _i]),
     "samrs_launch_count": (_i, [_vp, _i64p]),
@@ -260,6 +261,21 @@ class Engine:
             self._check(self._lib.samrs_rle_encode(self._h, src_m, src_l, B, H, W, counts.data_ptr(), int(capacity),
                                                    offsets.data_ptr(), area.data_ptr(), _stream(self.device)), "rle_encode")
         return counts, offsets, area[:B]
+
+    def rle_strings(self, counts: torch.Tensor, offsets: torch.Tensor, char_capacity: Optional[int] = None):
+        """Compressed COCO strings of the runs returned by `rle_encode`, on the device: `(chars uint8[char_capacity],
+        char_offsets int64[B+1])`; mask b's string is `bytes(chars[char_offsets[b]:char_offsets[b+1]])`.  A run needs at
+        most 7 characters; the default capacity is 2 per run + 64 per mask (real masks: ~1.3), check `char_offsets[-1]`."""
+        B = offsets.numel() - 1
+        cnt = counts if counts.dtype == torch.int32 else counts.to(torch.int32)
+        if char_capacity is None:
+            char_capacity = 2 * cnt.numel() + 64 * max(B, 1)
+        chars = torch.empty((max(1, char_capacity),), dtype=torch.uint8, device=self.device)
+        coff = torch.empty((B + 1,), dtype=torch.int64, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_rle_string(self._h, cnt.data_ptr(), offsets.data_ptr(), B, cnt.numel(), chars.data_ptr(),
+                                                   int(char_capacity), coff.data_ptr(), _stream(self.device)), "rle_string")
+        return chars, coff
 
     PROFILE_CATEGORIES = ("gemm_tc", "attn_window", "attn_global", "relpos", "layernorm", "encode_total", "decode_total", "epilogue")
 

@@ -93,17 +93,25 @@ def coco_string_decode(s: str) -> List[int]:
 
 def instance_records(counts: torch.Tensor, offsets: torch.Tensor, area: torch.Tensor, h: int, w: int, boxes: np.ndarray,
                      labels: Sequence[int], categories: Optional[Sequence[str]] = None, compressed: bool = True,
-                     rboxes: Optional[np.ndarray] = None) -> List[Dict[str, Any]]:
+                     rboxes: Optional[np.ndarray] = None, strings: Optional[Sequence[str]] = None) -> List[Dict[str, Any]]:
     """One dict per mask in the drivers' schema; `mask` is a COCO RLE dict (compressed string unless compressed=False).
 
     Without `rboxes`: `{mask, bbox, category, label, size}` (main_sam_hbox_semantic.py:204).  With `rboxes` (B,4,2), the
     rotated-box drivers' variant `{mask, rbox, rhbox, category, label, size}` (main_sam_rhbox_semantic.py:203-209), where
-    `boxes` are the polygons' enclosing horizontal boxes the masks were prompted with (`rhbox`, :120-130)."""
-    rles = to_rle_dicts(counts, offsets, h, w)
+    `boxes` are the polygons' enclosing horizontal boxes the masks were prompted with (`rhbox`, :120-130).
+    `strings`: the compressed strings when they were already produced on the device (`Engine.rle_strings`); `counts` may
+    then be None."""
     sizes = area.detach().cpu().numpy()
+    if strings is not None:
+        rles = [{"size": [int(h), int(w)], "counts": None} for _ in strings]
+    else:
+        rles = to_rle_dicts(counts, offsets, h, w)
     recs = []
     for j, r in enumerate(rles):
-        m = {"size": r["size"], "counts": coco_string(r["counts"]) if compressed else r["counts"]}
+        if strings is not None:
+            m = {"size": r["size"], "counts": strings[j]}
+        else:
+            m = {"size": r["size"], "counts": coco_string(r["counts"]) if compressed else r["counts"]}
         rec = {"mask": m}
         if rboxes is None:
             rec["bbox"] = np.asarray(boxes[j])
@@ -113,6 +121,15 @@ def instance_records(counts: torch.Tensor, offsets: torch.Tensor, area: torch.Te
                     "size": int(sizes[j])})
         recs.append(rec)
     return recs
+
+
+def strings_from_device(chars: torch.Tensor, char_offsets: torch.Tensor) -> List[str]:
+    """Per-mask compressed strings from `Engine.rle_strings` output (host copies of the used part only)."""
+    off = char_offsets.detach().cpu().numpy().astype(np.int64)
+    if off[-1] > chars.numel():
+        raise ValueError(f"rle: {int(off[-1])} characters do not fit the capacity of {chars.numel()}")
+    buf = chars[: int(off[-1])].detach().cpu().numpy().tobytes()
+    return [buf[off[b]:off[b + 1]].decode("ascii") for b in range(len(off) - 1)]
 
 
 def enclosing_hboxes(rboxes: np.ndarray) -> np.ndarray:

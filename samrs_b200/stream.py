@@ -82,8 +82,9 @@ def tile_outputs(predictor, engine, image: np.ndarray, boxes: torch.Tensor, labe
     encode: the label map (painter reduce) in `canvas` and, if `instance`, the run-length payload of every mask.
 
     Everything is enqueued on the current stream; nothing is copied to the host.  Returns `(canvas, payload)` with
-    `payload = [(counts, offsets, area, n_masks, capacity, source), ...]` per chunk (CUDA tensors; `source` = what was
-    encoded, kept so that `fetch_runs` can encode again should the runs not fit).  1024 x 1024 tiles use the
+    `payload = [(counts, offsets, area, n_masks, capacity, source, chars, char_offsets), ...]` per chunk (CUDA tensors;
+    `source` = what was encoded, kept so that `fetch_runs` can encode again should the runs not fit; `chars` = the
+    compressed COCO strings, also produced on the device).  1024 x 1024 tiles use the
     fused kernels (upsample + threshold + paint / + RLE straight from the 256 x 256 logits); other sizes go through the
     general postprocess and paint / encode the bool masks."""
     predictor.set_image(image)
@@ -99,13 +100,13 @@ def tile_outputs(predictor, engine, image: np.ndarray, boxes: torch.Tensor, labe
             engine.semantic_reduce(low, ldev[s:s + n], canvas)
             if instance:
                 cap = n * capacity_per_mask
-                payload.append(engine.rle_encode(low_res=low, capacity=cap) + (n, cap, ("low_res", low)))
+                payload.append(_encode(engine, n, cap, "low_res", low))
         else:
             masks = engine.postprocess(low, predictor.input_size, (H, W))
             engine.paint_masks(masks, ldev[s:s + n], canvas)
             if instance:
                 cap = n * capacity_per_mask
-                payload.append(engine.rle_encode(masks=masks, capacity=cap) + (n, cap, ("masks", masks)))
+                payload.append(_encode(engine, n, cap, "masks", masks))
     return canvas, payload
 
 
@@ -126,19 +127,26 @@ def instance_tile(predictor, engine, image: np.ndarray, boxes: torch.Tensor, lab
     return _records_from_payload(engine, payload, H, W, boxes.detach().cpu().numpy(), [int(v) for v in labels], categories, None)
 
 
+def _encode(engine, n, cap, kind, src):
+    counts, offsets, area = engine.rle_encode(capacity=cap, **{kind: src})
+    chars, coff = engine.rle_strings(counts, offsets, char_capacity=2 * cap + 64 * n)
+    return (counts, offsets, area, n, cap, (kind, src), chars, coff)
+
+
 def fetch_runs(engine, entry, reencode: bool = True):
-    """Host copies `(counts[:total], offsets, area)` of one payload entry.  Only the runs that exist are copied (the host
-    learns their number from `offsets[-1]`); if they did not fit the capacity the chunk is encoded again with the exact
-    size (noise-like masks - e.g. from the synthetic checkpoint - can have 100k+ runs each)."""
-    counts, offsets, area, n, cap, (kind, src) = entry
+    """`(area on the host, chars, char_offsets)` of one payload entry, after checking that runs and characters fit their
+    buffers; if not, the chunk is encoded again with the exact size (noise-like masks - e.g. from the synthetic checkpoint -
+    can have 100k+ runs each).  The run lengths themselves never travel: only the compressed strings are copied."""
+    counts, offsets, area, n, cap, (kind, src), chars, coff = entry
     off = offsets.cpu()
     total = int(off[-1])
-    if total > cap:
-        if not reencode:                                  # a second thread must not drive the engine: the caller sizes the buffer
-            raise RuntimeError(f"rle: {total} runs exceed the capacity of {cap} for {n} masks; raise capacity_per_mask")
+    if total > cap or int(coff[-1]) > chars.numel():
+        if not reencode:                                  # a second thread must not drive the engine: the caller sizes the buffers
+            raise RuntimeError(f"rle: {total} runs / {int(coff[-1])} characters exceed the capacity ({cap} runs) for {n} masks; "
+                               "raise capacity_per_mask")
         counts, offsets, area = engine.rle_encode(capacity=total, **{kind: src})
-        off = offsets.cpu()
-    return counts[:total].cpu(), off, area.cpu()
+        chars, coff = engine.rle_strings(counts, offsets, char_capacity=7 * total + 64)
+    return area.cpu(), chars, coff
 
 
 def _records_from_payload(engine, payload, H, W, boxes_np, labels, categories, rboxes_np, reencode: bool = True):
@@ -146,9 +154,10 @@ def _records_from_payload(engine, payload, H, W, boxes_np, labels, categories, r
     records, s = [], 0
     for entry in payload:
         n = entry[3]
-        counts, offsets, area = fetch_runs(engine, entry, reencode)
-        records += host_rle.instance_records(counts, offsets, area, H, W, boxes_np[s:s + n], labels[s:s + n], categories,
-                                             rboxes=None if rboxes_np is None else rboxes_np[s:s + n])
+        area, chars, coff = fetch_runs(engine, entry, reencode)
+        records += host_rle.instance_records(None, None, area, H, W, boxes_np[s:s + n], labels[s:s + n], categories,
+                                             rboxes=None if rboxes_np is None else rboxes_np[s:s + n],
+                                             strings=host_rle.strings_from_device(chars, coff))
         s += n
     return records
 
