@@ -1053,6 +1053,8 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
   return 0;
 }
 
+constexpr int T2I_CHUNKS = 4;     // key chunks of the token -> image attention (blocks = prompts x 8 heads x chunks)
+
 static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, int multimask) {
   const int BT = B * T;
   // image-side layer-0 operands: shared across prompts unless a mask prompt makes src per-prompt
@@ -1088,13 +1090,13 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
     SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, L.t2i.wq, 256, e->d_tmp128a, 128, L.t2i.bq, nullptr, 0, 0, BT, 128, 256, 0));
     if (layer == 0) {
-      t2i_attn_kernel<<<dim3(B, 8, 8), 256, 0, st>>>(e->d_tmp128a, K0, V0, 128, kv_stride, e->d_t2i_part, T);
+      t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128a, K0, V0, 128, kv_stride, e->d_t2i_part, T);
     } else {
       // K | V | Q(i2t) projections of the per-prompt image tokens in one tensor-core GEMM
       SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p1, M4, 384, 768, e->d_P, 384, e->bias_p1, e->R1, 384, 4096));
-      t2i_attn_kernel<<<dim3(B, 8, 8), 256, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 384, size_t(4096) * 384, e->d_t2i_part, T);
+      t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 384, size_t(4096) * 384, e->d_t2i_part, T);
     }
-    t2i_combine_kernel<<<(B * 8 * T * 16 + 255) / 256, 256, 0, st>>>(e->d_t2i_part, e->d_tmp128b, B, T);
+    t2i_combine_kernel<<<(B * 8 * T * 16 + 255) / 256, 256, 0, st>>>(e->d_t2i_part, e->d_tmp128b, B, T, T2I_CHUNKS);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch(2);
     SAMRS_TRY(sgemm(st, e->d_tmp128b, 128, L.t2i.wo, 128, queries, 256, L.t2i.bo, queries, 256, 0, BT, 256, 128, 0));
@@ -1108,9 +1110,9 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
     SAMRS_TRY(sgemm(st, qpl, 256, L.i2t.wk, 256, e->d_tmp128a, 128, L.i2t.bk, nullptr, 0, 0, BT, 128, 256, 0));
     SAMRS_TRY(sgemm(st, queries, 256, L.i2t.wv, 256, e->d_tmp128b, 128, L.i2t.bv, nullptr, 0, 0, BT, 128, 256, 0));
     if (layer == 0)
-      i2t_attn_kernel<<<dim3(4096 / 128, B), 128, size_t(2) * T * 128 * 4, st>>>(Qi0, 128, kv_stride, e->d_tmp128a, e->d_tmp128b, e->d_ioA, T);
+      i2t_attn_kernel<<<dim3(4096 * 8 / 256, B), 256, size_t(2) * T * 128 * 4, st>>>(Qi0, 128, kv_stride, e->d_tmp128a, e->d_tmp128b, e->d_ioA, T);
     else
-      i2t_attn_kernel<<<dim3(4096 / 128, B), 128, size_t(2) * T * 128 * 4, st>>>(e->d_P + 256, 384, size_t(4096) * 384, e->d_tmp128a,
+      i2t_attn_kernel<<<dim3(4096 * 8 / 256, B), 256, size_t(2) * T * 128 * 4, st>>>(e->d_P + 256, 384, size_t(4096) * 384, e->d_tmp128a,
                                                                                   e->d_tmp128b, e->d_ioA, T);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
@@ -1129,8 +1131,8 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
     SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, a.wq, 256, e->d_tmp128a, 128, a.bq, nullptr, 0, 0, BT, 128, 256, 0));
     SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p2, M4, 512, 768, e->d_P, 512, e->bias_p2, e->R2, 512, 4096));
-    t2i_attn_kernel<<<dim3(B, 8, 8), 256, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 512, size_t(4096) * 512, e->d_t2i_part, T);
-    t2i_combine_kernel<<<(B * 8 * T * 16 + 255) / 256, 256, 0, st>>>(e->d_t2i_part, e->d_tmp128b, B, T);
+    t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 512, size_t(4096) * 512, e->d_t2i_part, T);
+    t2i_combine_kernel<<<(B * 8 * T * 16 + 255) / 256, 256, 0, st>>>(e->d_t2i_part, e->d_tmp128b, B, T, T2I_CHUNKS);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch(2);
     SAMRS_TRY(sgemm(st, e->d_tmp128b, 128, a.wo, 128, queries, 256, a.bo, queries, 256, 0, BT, 256, 128, 0));

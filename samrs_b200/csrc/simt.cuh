@@ -564,91 +564,99 @@ __global__ void tok_self_attn_kernel(const float* __restrict__ q, const float* _
 }
 
 // (2) token -> image cross attention: q [B][T][128]; K,V rows of `ld` floats, prompt stride kv_bstride
-//     (0 = shared by all prompts); 8 heads x 16.  One block per (prompt, head, 512-key chunk): every thread keeps its
-//     two keys' K and V rows in registers and reuses them for all T query tokens, so K/V are read exactly once.
-//     Per-chunk softmax partials (max, sum, weighted V) go to `part`; t2i_combine_kernel merges the 8 chunks.
-__global__ void __launch_bounds__(256)
+//     (0 = shared by all prompts); 8 heads x 16.  One block per (prompt, head, key chunk of 4096 / gridDim.z keys), one WARP
+//     per query token: the block stages 128 keys' K and V head slices in shared memory (coalesced 64-byte row segments),
+//     lane l of every warp then owns keys l, l+32, ... of the tile and runs its own online softmax over them (running max,
+//     sum and 16 weighted-V accumulators in registers), so K/V are read once per block and nothing is reduced across
+//     threads until the very end: one 18-value warp merge per token.  The first version reduced 17 values across the
+//     block for every token and key pair (595 shuffles + 21 barriers per thread) and ran at 1.3 TB/s; this one is bound by
+//     the K/V read.  Per-chunk partials (acc[16], sum, max) go to `part`; t2i_combine_kernel merges the chunks.
+constexpr int T2I_TILE = 128;       // keys per shared-memory tile
+constexpr int T2I_PITCH = 20;       // floats per staged row (16 + 4 pad: conflict-free float4 reads at row stride 1)
+__global__ void __launch_bounds__(512)
 t2i_attn_kernel(const float* __restrict__ q, const float* __restrict__ K, const float* __restrict__ V, int ld,
-                size_t kv_bstride, float* __restrict__ part /*[B][8][T][8][18]*/, int T) {
-  const int b = blockIdx.x, h = blockIdx.y, ch = blockIdx.z, tid = threadIdx.x;
+                size_t kv_bstride, float* __restrict__ part /*[B][8][T][nch][18]*/, int T) {
+  const int b = blockIdx.x, h = blockIdx.y, ch = blockIdx.z, nch = gridDim.z;
+  const int tid = threadIdx.x, lane = tid & 31, t = tid >> 5;       // warp t = query token t (blockDim.x = 32 * T)
+  const int keys_per_chunk = 4096 / nch;
   const float* Kb = K + size_t(b) * kv_bstride + h * 16;
   const float* Vb = V + size_t(b) * kv_bstride + h * 16;
-  __shared__ float red[8][18];
-  __shared__ float sq[16 * 16];
-  for (int i = tid; i < T * 16; i += 256) sq[i] = q[(size_t(b) * T + i / 16) * 128 + h * 16 + i % 16];
-  float kr[2][16], vr[2][16];
+  __shared__ __align__(16) float sk[T2I_TILE * T2I_PITCH];
+  __shared__ __align__(16) float sv[T2I_TILE * T2I_PITCH];
+  float qv[16];
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const size_t key = size_t(ch) * 512 + tid + 256 * i;
-    const float4* kp = reinterpret_cast<const float4*>(Kb + key * ld);
-    const float4* vp = reinterpret_cast<const float4*>(Vb + key * ld);
+  for (int c = 0; c < 16; ++c) qv[c] = q[(size_t(b) * T + t) * 128 + h * 16 + c] * 0.25f;     // 1 / sqrt(16) folded into q
+  float m = -INFINITY, l = 0.f, acc[16];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 a = kp[j], c = vp[j];
-      kr[i][4 * j] = a.x; kr[i][4 * j + 1] = a.y; kr[i][4 * j + 2] = a.z; kr[i][4 * j + 3] = a.w;
-      vr[i][4 * j] = c.x; vr[i][4 * j + 1] = c.y; vr[i][4 * j + 2] = c.z; vr[i][4 * j + 3] = c.w;
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  for (int k0 = 0; k0 < keys_per_chunk; k0 += T2I_TILE) {
+    __syncthreads();                                                 // previous tile consumed
+    for (int i = tid; i < T2I_TILE * 4; i += blockDim.x) {           // 4 float4 per key row and operand
+      const int r = i >> 2, c4 = i & 3;
+      const size_t key = size_t(ch) * keys_per_chunk + k0 + r;
+      *reinterpret_cast<float4*>(sk + r * T2I_PITCH + 4 * c4) = *(reinterpret_cast<const float4*>(Kb + key * ld) + c4);
+      *reinterpret_cast<float4*>(sv + r * T2I_PITCH + 4 * c4) = *(reinterpret_cast<const float4*>(Vb + key * ld) + c4);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < T2I_TILE / 32; ++j) {
+      const float* kr = sk + (lane + 32 * j) * T2I_PITCH;
+      const float* vr = sv + (lane + 32 * j) * T2I_PITCH;
+      float sc = 0.f;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 kk = *reinterpret_cast<const float4*>(kr + 4 * c4);
+        sc = fmaf(qv[4 * c4], kk.x, sc); sc = fmaf(qv[4 * c4 + 1], kk.y, sc); sc = fmaf(qv[4 * c4 + 2], kk.z, sc); sc = fmaf(qv[4 * c4 + 3], kk.w, sc);
+      }
+      if (sc > m) {                                                  // new running max: rescale what has been accumulated
+        const float a = expf(m - sc);                                // exp(-inf) = 0 on the first key
+        l *= a;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] *= a;
+        m = sc;
+      }
+      const float pr = expf(sc - m);
+      l += pr;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        const float4 vv = *reinterpret_cast<const float4*>(vr + 4 * c4);
+        acc[4 * c4] = fmaf(pr, vv.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(pr, vv.y, acc[4 * c4 + 1]);
+        acc[4 * c4 + 2] = fmaf(pr, vv.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(pr, vv.w, acc[4 * c4 + 3]);
+      }
     }
   }
-  __syncthreads();
-  for (int t = 0; t < T; ++t) {
-    float s0 = 0.f, s1 = 0.f;
+  // merge the 32 lanes' (max, sum, acc) of this token
+  float M = m;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const float qc = sq[t * 16 + c];
-      s0 = fmaf(qc, kr[0][c], s0);
-      s1 = fmaf(qc, kr[1][c], s1);
-    }
-    s0 *= 0.25f;                          // / sqrt(16)
-    s1 *= 0.25f;
-    float m = fmaxf(s0, s1);
+  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  const float w = expf(m - M);
+  l *= w;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if ((tid & 31) == 0) red[tid >> 5][17] = m;
-    __syncthreads();
-    m = red[0][17];
+  for (int c = 0; c < 16; ++c) acc[c] *= w;
 #pragma unroll
-    for (int w = 1; w < 8; ++w) m = fmaxf(m, red[w][17]);
-    const float p0 = expf(s0 - m), p1 = expf(s1 - m);
-    float l = p0 + p1;
-    float acc[16];
+  for (int o = 16; o > 0; o >>= 1) {
+    l += __shfl_xor_sync(0xffffffffu, l, o);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = fmaf(p0, vr[0][c], p1 * vr[1][c]);
+    for (int c = 0; c < 16; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
+  }
+  if (lane == 0) {
+    float* o = part + ((((size_t(b) * 8 + h) * T + t) * nch) + ch) * 18;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      l += __shfl_xor_sync(0xffffffffu, l, o);
-#pragma unroll
-      for (int c = 0; c < 16; ++c) acc[c] += __shfl_xor_sync(0xffffffffu, acc[c], o);
-    }
-    __syncthreads();                       // everyone has read red[][17]
-    if ((tid & 31) == 0) {
-      red[tid >> 5][16] = l;
-#pragma unroll
-      for (int c = 0; c < 16; ++c) red[tid >> 5][c] = acc[c];
-    }
-    __syncthreads();
-    if (tid < 18) {
-      float v = 0.f;
-      if (tid == 17) v = m;
-      else
-#pragma unroll
-        for (int w = 0; w < 8; ++w) v += red[w][tid];
-      part[((((size_t(b) * 8 + h) * T + t) * 8) + ch) * 18 + tid] = v;
-    }
-    __syncthreads();
+    for (int c = 0; c < 16; ++c) o[c] = acc[c];
+    o[16] = l;
+    o[17] = M;
   }
 }
-// merge the 8 key-chunk partials: out[b][t][h*16 + c] = sum_i acc_i e^(m_i - M) / sum_i l_i e^(m_i - M)
-__global__ void t2i_combine_kernel(const float* __restrict__ part, float* __restrict__ out /*[B][T][128]*/, int B, int T) {
+// merge the key-chunk partials: out[b][t][h*16 + c] = sum_i acc_i e^(m_i - M) / sum_i l_i e^(m_i - M)
+__global__ void t2i_combine_kernel(const float* __restrict__ part, float* __restrict__ out /*[B][T][128]*/, int B, int T, int nch) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;       // (b, h, t, c)
   if (i >= B * 8 * T * 16) return;
   const int c = i % 16, t = (i / 16) % T, h = (i / (16 * T)) % 8, b = i / (16 * T * 8);
-  const float* p = part + (((size_t(b) * 8 + h) * T + t) * 8) * 18;
+  const float* p = part + (((size_t(b) * 8 + h) * T + t) * nch) * 18;
   float M = -INFINITY;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) M = fmaxf(M, p[k * 18 + 17]);
+  for (int k = 0; k < nch; ++k) M = fmaxf(M, p[k * 18 + 17]);
   float num = 0.f, den = 0.f;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
+  for (int k = 0; k < nch; ++k) {
     const float w = expf(p[k * 18 + 17] - M);
     num = fmaf(p[k * 18 + c], w, num);
     den = fmaf(p[k * 18 + 16], w, den);
@@ -663,10 +671,10 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 }
 
 // (3) image -> token cross attention: Q rows of `ldq` floats, prompt stride q_bstride (0 = shared); k,v [B][T][128];
-//     one thread per (prompt, image token) looping over the 8 heads, so the prompt's k,v in smem are read as warp-wide
-//     broadcasts.  The result feeds the out_proj tensor-core GEMM and is written directly as the split-fp16 operand
-//     [B*4096][hi(128) | lo(128) | hi(128)].
-__global__ void __launch_bounds__(128)
+//     one thread per (prompt, image token, head): the 8 threads of a token read its 512-byte Q row and write the three
+//     256-byte segments of its output row together (coalesced), the prompt's k,v sit in shared memory.  The result feeds
+//     the out_proj tensor-core GEMM and is written directly as the split-fp16 operand [B*4096][hi(128) | lo(128) | hi(128)].
+__global__ void __launch_bounds__(256)
 i2t_attn_kernel(const float* __restrict__ Q, int ldq, size_t q_bstride, const float* __restrict__ k, const float* __restrict__ v,
                 __half* __restrict__ out_split /*[B][4096][384]*/, int T) {
   extern __shared__ float sm[];
@@ -678,59 +686,57 @@ i2t_attn_kernel(const float* __restrict__ Q, int ldq, size_t q_bstride, const fl
     sv[i] = v[size_t(b) * T * 128 + i];
   }
   __syncthreads();
-  const int token = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gi = blockIdx.x * blockDim.x + threadIdx.x;         // (token, head)
+  const int token = gi >> 3, h = gi & 7;
   const float* qrow = Q + size_t(b) * q_bstride + size_t(token) * ldq;
   __half* orow = out_split + (size_t(b) * 4096 + token) * 384;
-#pragma unroll 1
-  for (int h = 0; h < 8; ++h) {
-    const float4* qr = reinterpret_cast<const float4*>(qrow + h * 16);
-    const float4 q0 = qr[0], q1 = qr[1], q2 = qr[2], q3 = qr[3];
-    const float qv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-    float m = -INFINITY;
-    for (int t = 0; t < T; ++t) {
-      const float4* kk = reinterpret_cast<const float4*>(sk + t * 128 + h * 16);
-      float a = 0.f;
+  const float4* qr = reinterpret_cast<const float4*>(qrow + h * 16);
+  const float4 q0 = qr[0], q1 = qr[1], q2 = qr[2], q3 = qr[3];
+  const float qv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+  float m = -INFINITY;
+  for (int t = 0; t < T; ++t) {
+    const float4* kk = reinterpret_cast<const float4*>(sk + t * 128 + h * 16);
+    float a = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 w = kk[j];
-        a = fmaf(qv[4 * j], w.x, a); a = fmaf(qv[4 * j + 1], w.y, a); a = fmaf(qv[4 * j + 2], w.z, a); a = fmaf(qv[4 * j + 3], w.w, a);
-      }
-      m = fmaxf(m, a * 0.25f);
+    for (int j = 0; j < 4; ++j) {
+      const float4 w = kk[j];
+      a = fmaf(qv[4 * j], w.x, a); a = fmaf(qv[4 * j + 1], w.y, a); a = fmaf(qv[4 * j + 2], w.z, a); a = fmaf(qv[4 * j + 3], w.w, a);
     }
-    float l = 0.f;
-    float acc[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-    for (int t = 0; t < T; ++t) {
-      const float4* kk = reinterpret_cast<const float4*>(sk + t * 128 + h * 16);
-      const float4* vv = reinterpret_cast<const float4*>(sv + t * 128 + h * 16);
-      float a = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 w = kk[j];
-        a = fmaf(qv[4 * j], w.x, a); a = fmaf(qv[4 * j + 1], w.y, a); a = fmaf(qv[4 * j + 2], w.z, a); a = fmaf(qv[4 * j + 3], w.w, a);
-      }
-      const float pexp = expf(a * 0.25f - m);
-      l += pexp;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float4 w = vv[j];
-        acc[4 * j] = fmaf(pexp, w.x, acc[4 * j]); acc[4 * j + 1] = fmaf(pexp, w.y, acc[4 * j + 1]);
-        acc[4 * j + 2] = fmaf(pexp, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(pexp, w.w, acc[4 * j + 3]);
-      }
-    }
-    const float inv = 1.0f / l;
-    __half hi[16], lo[16];
-#pragma unroll
-    for (int c = 0; c < 16; ++c) split_f16(acc[c] * inv, hi[c], lo[c]);
-    __half* o = orow + h * 16;
-    reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(hi)[0];
-    reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(hi)[1];
-    reinterpret_cast<uint4*>(o + 128)[0] = reinterpret_cast<uint4*>(lo)[0];
-    reinterpret_cast<uint4*>(o + 128)[1] = reinterpret_cast<uint4*>(lo)[1];
-    reinterpret_cast<uint4*>(o + 256)[0] = reinterpret_cast<uint4*>(hi)[0];
-    reinterpret_cast<uint4*>(o + 256)[1] = reinterpret_cast<uint4*>(hi)[1];
+    m = fmaxf(m, a * 0.25f);
   }
+  float l = 0.f;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+  for (int t = 0; t < T; ++t) {
+    const float4* kk = reinterpret_cast<const float4*>(sk + t * 128 + h * 16);
+    const float4* vv = reinterpret_cast<const float4*>(sv + t * 128 + h * 16);
+    float a = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 w = kk[j];
+      a = fmaf(qv[4 * j], w.x, a); a = fmaf(qv[4 * j + 1], w.y, a); a = fmaf(qv[4 * j + 2], w.z, a); a = fmaf(qv[4 * j + 3], w.w, a);
+    }
+    const float pexp = expf(a * 0.25f - m);
+    l += pexp;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 w = vv[j];
+      acc[4 * j] = fmaf(pexp, w.x, acc[4 * j]); acc[4 * j + 1] = fmaf(pexp, w.y, acc[4 * j + 1]);
+      acc[4 * j + 2] = fmaf(pexp, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(pexp, w.w, acc[4 * j + 3]);
+    }
+  }
+  const float inv = 1.0f / l;
+  __half hi[16], lo[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) split_f16(acc[c] * inv, hi[c], lo[c]);
+  __half* o = orow + h * 16;
+  reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(hi)[0];
+  reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(hi)[1];
+  reinterpret_cast<uint4*>(o + 128)[0] = reinterpret_cast<uint4*>(lo)[0];
+  reinterpret_cast<uint4*>(o + 128)[1] = reinterpret_cast<uint4*>(lo)[1];
+  reinterpret_cast<uint4*>(o + 256)[0] = reinterpret_cast<uint4*>(hi)[0];
+  reinterpret_cast<uint4*>(o + 256)[1] = reinterpret_cast<uint4*>(hi)[1];
 }
 
 // LayerNorm over 256 channels (decoder norm4, eps 1e-5) writing the fp32 result (optional) and its split-fp16
