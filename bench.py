@@ -275,6 +275,10 @@ class Rig:
         for _ in range(NS):
             e_ = Engine(VARIANT, device)
             e_.load_state_dict(sd)
+            if os.environ.get("SAMRS_PDL") == "0":         # A/B switches (defaults: CUDA graphs and PDL on)
+                e_.set_pdl(False)
+            if os.environ.get("SAMRS_GRAPHS") == "0":
+                e_.set_graphs(False)
             self.engines.append(e_)
         del sd
         torch.cuda.empty_cache()

@@ -60,6 +60,13 @@ int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int i
 int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_ids, int B,
                           uint8_t* label_map_inout, int H, int W, void* stream);
 
+/* rotated boxes -> mask prompts on the device: replaces the per-box OpenCV loop of
+ * main_sam_rbox_mask_instance.py:125-141 (fillPoly of the int-truncated polygon, +-1000, resize to long side 1024, pad with
+ * -1000, resize to 256 x 256).  polys (B,4,2) float in original-image pixels -> out (B,256,256) float = the `mask_input` of
+ * predict_torch.  fillPoly's raster is reproduced bit for bit, the two INTER_LINEAR passes to within one float32 ulp
+ * (see csrc/rbox.cuh).  *status_out (device int) becomes 1 if a vertex lies outside the image (not supported). */
+int samrs_rbox_mask_prompts(void* engine, const float* polys, int B, int H, int W, float* out, int* status_out, void* stream);
+
 /* the same painter reduce over bool masks of any size (tiles whose original size is not 1024 x 1024: the masks come from
  * samrs_postprocess): main_sam_hbox_semantic.py:195-199; highest box index wins, composes across chunks. */
 int samrs_paint_masks(void* engine, const uint8_t* masks /*[B][H][W]*/, const int* class_ids, int B, int H, int W,
@@ -101,6 +108,12 @@ int samrs_profile(void* engine, int enable, float* ms_by_category, int* launches
  * graphs afterwards (launches that touch caller-owned buffers stay outside; profiling runs eagerly).  enable = 0 drops
  * the graphs and launches every kernel directly. */
 int samrs_set_graphs(void* engine, int enable);
+
+/* programmatic dependent launch (default on): the tcgen05 GEMM, attention and LayerNorm kernels are launched with
+ * cudaLaunchAttributeProgrammaticStreamSerialization and wait for their predecessor themselves (griddepcontrol.wait) after
+ * their own prologue, so barrier / tensor-memory set-up overlaps the previous kernel's tail.  enable = 0 restores plain
+ * stream order for A/B measurements. */
+int samrs_set_pdl(void* engine, int enable);
 
 /* kernels launched by this engine since creation (bench.py's gpu_launches). */
 int samrs_launch_count(void* engine, int64_t* count_out);

@@ -175,6 +175,8 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // the two softmax warpgroups get 200 (128*96 + 256*200 = 63488 <= 384*168, the pool the CTA was launched with)
   if (warp < 4) asm volatile("setmaxnreg.dec.sync.aligned.u32 96;");
   else asm volatile("setmaxnreg.inc.sync.aligned.u32 200;");
+  pdl_trigger();
+  pdl_wait();                                           // zero fill, selector matrix, barriers and TMEM came before
 
   auto unit_coords = [&](int unit, int& head, int& qy0, int& qy1, int& x0, int& ky0) {
     head = unit % p.heads;

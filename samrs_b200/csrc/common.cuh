@@ -60,6 +60,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its predecessor in
+// the stream is still running: pdl_trigger() (executed by every CTA of the predecessor, here at its very start) lets the
+// next grid's CTAs be scheduled into whatever SM resources free up, pdl_wait() blocks until the predecessor grid has
+// completed and its memory is visible.  Everything before pdl_wait() - barrier init, TMEM allocation, descriptor prefetch,
+// constant tables - overlaps the predecessor's tail; nothing that reads or writes activations may precede it.
+// Both are no-ops in a kernel launched without the attribute.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -16,6 +16,7 @@
 #include "gemm_tc2.cuh"
 #include "simt.cuh"
 #include "rle.cuh"
+#include "rbox.cuh"
 
 namespace samrs {
 
@@ -117,11 +118,25 @@ struct LaunchCtx {
   size_t splitk_ws_floats = 0;
   std::unordered_set<const void*> smem_opted;     // kernels whose dynamic-smem limit was raised on this engine's device
   bool capturing = false;                         // a CUDA graph is being captured: no events, no attribute calls
+  bool pdl = true;                                // programmatic dependent launch for the kernels that support it
 };
 static thread_local LaunchCtx* t_ctx = nullptr;
 static inline void count_launch(int n = 1) {
   if (t_ctx) t_ctx->launches += n;
 }
+// launch with programmatic stream serialization (see common.cuh): only for kernels that call pdl_wait() themselves
+static bool g_pdl_default = true;
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = (t_ctx ? t_ctx->pdl : g_pdl_default) ? 1 : 0;
+  cfg.attrs = at; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <typename K>
 static int opt_in_smem(K kernel, int bytes) {
   const void* key = reinterpret_cast<const void*>(kernel);
@@ -135,8 +150,7 @@ template <int BN, bool OH, int ACT>
 static int launch_gemm_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = GemmCfg<BN>;
   SAMRS_TRY(opt_in_smem(gemm_tc_kernel<BN, OH, ACT>, Cfg::kSmemBytes));
-  gemm_tc_kernel<BN, OH, ACT><<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(tA, tB, tC, p);
-  SAMRS_CUDA_OK(cudaGetLastError());
+  SAMRS_CUDA_OK(launch_pdl(gemm_tc_kernel<BN, OH, ACT>, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, tA, tB, tC, p));
   count_launch();
   return 0;
 }
@@ -167,8 +181,7 @@ template <int BN, bool OH, int ACT>
 static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   SAMRS_TRY(opt_in_smem(gemm_tc2_kernel<BN, OH, ACT>, Cfg::kSmemBytes));
-  gemm_tc2_kernel<BN, OH, ACT><<<grid, GEMM_THREADS, Cfg::kSmemBytes, st>>>(tA, tB, tC, p);
-  SAMRS_CUDA_OK(cudaGetLastError());
+  SAMRS_CUDA_OK(launch_pdl(gemm_tc2_kernel<BN, OH, ACT>, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, tA, tB, tC, p));
   count_launch();
   return 0;
 }
@@ -381,6 +394,8 @@ struct Engine {
   unsigned long long resize_clock = 0;
   uint8_t* resize_tmp = nullptr;       // horizontal-pass result [H][out_w][3]
   size_t resize_tmp_bytes = 0;
+  uint8_t* rbox_mask = nullptr;        // rotated-box rasteriser scratch: [B][H][W] fill masks
+  size_t rbox_mask_bytes = 0;
   uint32_t* rle_packed = nullptr;      // run-length encoder scratch: column-major bit planes [B][ceil(H/32)][W]
   size_t rle_packed_words = 0;
   long long* rle_runs = nullptr;       // [rle_runs_cap] runs per mask
@@ -505,10 +520,10 @@ static int ln_rows(cudaStream_t st, const float* in, int ld_in, const float* g, 
   if constexpr (sizeof(OutT) == 2 && ACT == 0) {
     if (rows >= 1024 && (C == 1280 || C == 1024 || C == 768)) {
       const int g4 = (rows + 3) / 4;
-      if (C == 1280) ln_rows_stream_kernel<10><<<g4, 64, 0, st>>>(in, ld_in, g, b, eps, reinterpret_cast<__half*>(out), ld_out, rows);
-      else if (C == 1024) ln_rows_stream_kernel<8><<<g4, 64, 0, st>>>(in, ld_in, g, b, eps, reinterpret_cast<__half*>(out), ld_out, rows);
-      else ln_rows_stream_kernel<6><<<g4, 64, 0, st>>>(in, ld_in, g, b, eps, reinterpret_cast<__half*>(out), ld_out, rows);
-      SAMRS_CUDA_OK(cudaGetLastError());
+      __half* o16 = reinterpret_cast<__half*>(out);
+      if (C == 1280) SAMRS_CUDA_OK(launch_pdl(ln_rows_stream_kernel<10>, dim3(g4), dim3(64), 0, st, in, ld_in, g, b, eps, o16, ld_out, rows));
+      else if (C == 1024) SAMRS_CUDA_OK(launch_pdl(ln_rows_stream_kernel<8>, dim3(g4), dim3(64), 0, st, in, ld_in, g, b, eps, o16, ld_out, rows));
+      else SAMRS_CUDA_OK(launch_pdl(ln_rows_stream_kernel<6>, dim3(g4), dim3(64), 0, st, in, ld_in, g, b, eps, o16, ld_out, rows));
       count_launch();
       return 0;
     }
@@ -529,8 +544,7 @@ static int launch_attn2_inst(const CUtensorMap& tQ, const CUtensorMap& tKV, cons
   SAMRS_TRY(opt_in_smem(attn_tc2_kernel<HD, BX, QBY, KBY, NKT>, C::kSmemBytes));
   const int units = p.num_qtiles * p.heads;
   const int grid = units < num_sms ? units : num_sms;
-  attn_tc2_kernel<HD, BX, QBY, KBY, NKT><<<grid, 384, C::kSmemBytes, st>>>(tQ, tKV, tT, p);
-  SAMRS_CUDA_OK(cudaGetLastError());
+  SAMRS_CUDA_OK(launch_pdl(attn_tc2_kernel<HD, BX, QBY, KBY, NKT>, dim3(grid), dim3(384), C::kSmemBytes, st, tQ, tKV, tT, p));
   count_launch();
   return 0;
 }
@@ -1110,9 +1124,9 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
     SAMRS_TRY(sgemm(st, qpl, 256, L.i2t.wk, 256, e->d_tmp128a, 128, L.i2t.bk, nullptr, 0, 0, BT, 128, 256, 0));
     SAMRS_TRY(sgemm(st, queries, 256, L.i2t.wv, 256, e->d_tmp128b, 128, L.i2t.bv, nullptr, 0, 0, BT, 128, 256, 0));
     if (layer == 0)
-      i2t_attn_kernel<<<dim3(4096 * 8 / 256, B), 256, size_t(2) * T * 128 * 4, st>>>(Qi0, 128, kv_stride, e->d_tmp128a, e->d_tmp128b, e->d_ioA, T);
+      i2t_attn_kernel<<<dim3(4096 / 128, B), 128, size_t(2) * T * 128 * 4, st>>>(Qi0, 128, kv_stride, e->d_tmp128a, e->d_tmp128b, e->d_ioA, T);
     else
-      i2t_attn_kernel<<<dim3(4096 * 8 / 256, B), 256, size_t(2) * T * 128 * 4, st>>>(e->d_P + 256, 384, size_t(4096) * 384, e->d_tmp128a,
+      i2t_attn_kernel<<<dim3(4096 / 128, B), 128, size_t(2) * T * 128 * 4, st>>>(e->d_P + 256, 384, size_t(4096) * 384, e->d_tmp128a,
                                                                                   e->d_tmp128b, e->d_ioA, T);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
@@ -1470,6 +1484,33 @@ int samrs_rle_string(void* engine, const uint32_t* counts, const long long* offs
   return 0;
 }
 
+int samrs_rbox_mask_prompts(void* engine, const float* polys, int B, int H, int W, float* out, int* status_out, void* stream) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  LaunchScope ls(e);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (B < 0 || H < 1 || W < 1 || H > 16384 || W > 16384 || !out || !status_out || (B > 0 && !polys))
+    return set_err(e, samrs::fail(__FILE__, __LINE__, "rbox_mask_prompts: bad shape or null pointer"));
+  SAMRS_CUDA_OK(cudaMemsetAsync(status_out, 0, sizeof(int), st));
+  if (B == 0) return 0;
+  const size_t need = size_t(B) * H * W;
+  if (need > e->rbox_mask_bytes) {
+    e->release(&e->rbox_mask);
+    if (e->alloc(&e->rbox_mask, need) != 0) return set_err(e, 1);
+    e->rbox_mask_bytes = need;
+  }
+  SAMRS_CUDA_OK(cudaMemsetAsync(e->rbox_mask, 0, need, st));
+  // ResizeLongestSide.get_preprocess_shape (SA/utils/transforms.py:94-102): the size the driver resizes the +-1000 mask to
+  const double scale = 1024.0 / double(H > W ? H : W);
+  const int nh = int(H * scale + 0.5), nw = int(W * scale + 0.5);
+  rbox_fill_kernel<<<B, 256, 0, st>>>(polys, H, W, e->rbox_mask, status_out);
+  rbox_prompt_kernel<<<dim3(1, 256, B), 256, 0, st>>>(e->rbox_mask, H, W, nh, nw, out);
+  count_launch(2);
+  if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "rbox_mask_prompts launch failed"));
+  return 0;
+}
+
 int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_ids, int B, uint8_t* label_map, int H, int W, void* stream) {
   Engine* e = static_cast<Engine*>(engine);
   if (!e) return 1;
@@ -1519,6 +1560,16 @@ int samrs_profile(void* engine, int enable, float* ms_by_category, int* launches
     e->ctx.prof.pool.push_back(r.a); e->ctx.prof.pool.push_back(r.b);
   }
   e->ctx.prof.recs.clear();
+  return 0;
+}
+
+int samrs_set_pdl(void* engine, int enable) {
+  Engine* e = static_cast<Engine*>(engine);
+  if (!e) return 1;
+  cudaSetDevice(e->device);
+  cudaDeviceSynchronize();
+  e->ctx.pdl = enable != 0;
+  e->drop_graphs();                                  // captured launches carry the attribute
   return 0;
 }
 

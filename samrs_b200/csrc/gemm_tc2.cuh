@@ -71,6 +71,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) gemm_dbg(p, 1);
+  pdl_trigger();
+  pdl_wait();                                       // the prologue above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ---------------------------------------------------------------- TMA producer (both CTAs)

@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(64) ln_rows_stream_kernel(const float* __restr
                                                             int ld_out, int rows) {
   const int lane = threadIdx.x & 31;
   const int row0 = blockIdx.x * 4 + (threadIdx.x >> 5) * 2;
+  pdl_trigger();
+  pdl_wait();
   if (row0 >= rows) return;
   constexpr float Cf = float(128 * MAXV);
   float4 v[2][MAXV];
@@ -671,10 +673,10 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 }
 
 // (3) image -> token cross attention: Q rows of `ldq` floats, prompt stride q_bstride (0 = shared); k,v [B][T][128];
-//     one thread per (prompt, image token, head): the 8 threads of a token read its 512-byte Q row and write the three
-//     256-byte segments of its output row together (coalesced), the prompt's k,v sit in shared memory.  The result feeds
-//     the out_proj tensor-core GEMM and is written directly as the split-fp16 operand [B*4096][hi(128) | lo(128) | hi(128)].
-__global__ void __launch_bounds__(256)
+//     one thread per (prompt, image token) looping over the 8 heads, so the prompt's k,v in smem are read as warp-wide
+//     broadcasts.  The result feeds the out_proj tensor-core GEMM and is written directly as the split-fp16 operand
+//     [B*4096][hi(128) | lo(128) | hi(128)].
+__global__ void __launch_bounds__(128)
 i2t_attn_kernel(const float* __restrict__ Q, int ldq, size_t q_bstride, const float* __restrict__ k, const float* __restrict__ v,
                 __half* __restrict__ out_split /*[B][4096][384]*/, int T) {
   extern __shared__ float sm[];
@@ -686,57 +688,59 @@ i2t_attn_kernel(const float* __restrict__ Q, int ldq, size_t q_bstride, const fl
     sv[i] = v[size_t(b) * T * 128 + i];
   }
   __syncthreads();
-  const int gi = blockIdx.x * blockDim.x + threadIdx.x;         // (token, head)
-  const int token = gi >> 3, h = gi & 7;
+  const int token = blockIdx.x * blockDim.x + threadIdx.x;
   const float* qrow = Q + size_t(b) * q_bstride + size_t(token) * ldq;
   __half* orow = out_split + (size_t(b) * 4096 + token) * 384;
-  const float4* qr = reinterpret_cast<const float4*>(qrow + h * 16);
-  const float4 q0 = qr[0], q1 = qr[1], q2 = qr[2], q3 = qr[3];
-  const float qv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
-  float m = -INFINITY;
-  for (int t = 0; t < T; ++t) {
-    const float4* kk = reinterpret_cast<const float4*>(sk + t * 128 + h * 16);
-    float a = 0.f;
+#pragma unroll 1
+  for (int h = 0; h < 8; ++h) {
+    const float4* qr = reinterpret_cast<const float4*>(qrow + h * 16);
+    const float4 q0 = qr[0], q1 = qr[1], q2 = qr[2], q3 = qr[3];
+    const float qv[16] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w, q3.x, q3.y, q3.z, q3.w};
+    float m = -INFINITY;
+    for (int t = 0; t < T; ++t) {
+      const float4* kk = reinterpret_cast<const float4*>(sk + t * 128 + h * 16);
+      float a = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 w = kk[j];
-      a = fmaf(qv[4 * j], w.x, a); a = fmaf(qv[4 * j + 1], w.y, a); a = fmaf(qv[4 * j + 2], w.z, a); a = fmaf(qv[4 * j + 3], w.w, a);
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = kk[j];
+        a = fmaf(qv[4 * j], w.x, a); a = fmaf(qv[4 * j + 1], w.y, a); a = fmaf(qv[4 * j + 2], w.z, a); a = fmaf(qv[4 * j + 3], w.w, a);
+      }
+      m = fmaxf(m, a * 0.25f);
     }
-    m = fmaxf(m, a * 0.25f);
+    float l = 0.f;
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.f;
+    for (int t = 0; t < T; ++t) {
+      const float4* kk = reinterpret_cast<const float4*>(sk + t * 128 + h * 16);
+      const float4* vv = reinterpret_cast<const float4*>(sv + t * 128 + h * 16);
+      float a = 0.f;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = kk[j];
+        a = fmaf(qv[4 * j], w.x, a); a = fmaf(qv[4 * j + 1], w.y, a); a = fmaf(qv[4 * j + 2], w.z, a); a = fmaf(qv[4 * j + 3], w.w, a);
+      }
+      const float pexp = expf(a * 0.25f - m);
+      l += pexp;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float4 w = vv[j];
+        acc[4 * j] = fmaf(pexp, w.x, acc[4 * j]); acc[4 * j + 1] = fmaf(pexp, w.y, acc[4 * j + 1]);
+        acc[4 * j + 2] = fmaf(pexp, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(pexp, w.w, acc[4 * j + 3]);
+      }
+    }
+    const float inv = 1.0f / l;
+    __half hi[16], lo[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) split_f16(acc[c] * inv, hi[c], lo[c]);
+    __half* o = orow + h * 16;
+    reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(hi)[0];
+    reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(hi)[1];
+    reinterpret_cast<uint4*>(o + 128)[0] = reinterpret_cast<uint4*>(lo)[0];
+    reinterpret_cast<uint4*>(o + 128)[1] = reinterpret_cast<uint4*>(lo)[1];
+    reinterpret_cast<uint4*>(o + 256)[0] = reinterpret_cast<uint4*>(hi)[0];
+    reinterpret_cast<uint4*>(o + 256)[1] = reinterpret_cast<uint4*>(hi)[1];
   }
-  float l = 0.f;
-  float acc[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = 0.f;
-  for (int t = 0; t < T; ++t) {
-    const float4* kk = reinterpret_cast<const float4*>(sk + t * 128 + h * 16);
-    const float4* vv = reinterpret_cast<const float4*>(sv + t * 128 + h * 16);
-    float a = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 w = kk[j];
-      a = fmaf(qv[4 * j], w.x, a); a = fmaf(qv[4 * j + 1], w.y, a); a = fmaf(qv[4 * j + 2], w.z, a); a = fmaf(qv[4 * j + 3], w.w, a);
-    }
-    const float pexp = expf(a * 0.25f - m);
-    l += pexp;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float4 w = vv[j];
-      acc[4 * j] = fmaf(pexp, w.x, acc[4 * j]); acc[4 * j + 1] = fmaf(pexp, w.y, acc[4 * j + 1]);
-      acc[4 * j + 2] = fmaf(pexp, w.z, acc[4 * j + 2]); acc[4 * j + 3] = fmaf(pexp, w.w, acc[4 * j + 3]);
-    }
-  }
-  const float inv = 1.0f / l;
-  __half hi[16], lo[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) split_f16(acc[c] * inv, hi[c], lo[c]);
-  __half* o = orow + h * 16;
-  reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(hi)[0];
-  reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(hi)[1];
-  reinterpret_cast<uint4*>(o + 128)[0] = reinterpret_cast<uint4*>(lo)[0];
-  reinterpret_cast<uint4*>(o + 128)[1] = reinterpret_cast<uint4*>(lo)[1];
-  reinterpret_cast<uint4*>(o + 256)[0] = reinterpret_cast<uint4*>(hi)[0];
-  reinterpret_cast<uint4*>(o + 256)[1] = reinterpret_cast<uint4*>(hi)[1];
 }
 
 // LayerNorm over 256 channels (decoder norm4, eps 1e-5) writing the fp32 result (optional) and its split-fp16

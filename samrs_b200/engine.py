@@ -28,12 +28,14 @@ ABI = {
     "samrs_decode": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _i, _i, _vp, _vp, _vp]),
     "samrs_postprocess": (_i, [_vp, _vp, _i, _i, _i, _i, _i, _vp, _vp, _vp]),
     "samrs_semantic_reduce": (_i, [_vp, _vp, _vp, _i, _vp, _i, _i, _vp]),
+    "samrs_rbox_mask_prompts": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "samrs_paint_masks": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, _vp]),
     "samrs_resize_bilinear_u8": (_i, [_vp, _vp, _i, _i, _vp, _i, _i, _vp]),
     "samrs_rle_encode": (_i, [_vp, _vp, _vp, _i, _i, _i, _vp, ctypes.c_longlong, _vp, _vp, _vp]),
     "samrs_rle_string": (_i, [_vp, _vp, _vp, _i, ctypes.c_longlong, _vp, ctypes.c_longlong, _vp, _vp]),
     "samrs_profile": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _i]),
     "samrs_set_graphs": (_i, [_vp, _i]),
+    "samrs_set_pdl": (_i, [_vp, _i]),
     "samrs_launch_count": (_i, [_vp, _i64p]),
     "samrs_last_error": (ctypes.c_char_p, [_vp]),
     "samrs_destroy": (None, [_vp]),
@@ -200,6 +202,21 @@ class Engine:
                                                         label_map.shape[0], label_map.shape[1], _stream(self.device)), "semantic_reduce")
         return label_map
 
+    def rbox_mask_prompts(self, polys: torch.Tensor, image_hw: Sequence[int], check: bool = True) -> torch.Tensor:
+        """(B,4,2) rotated-box polygons in original-image pixels -> (B,1,256,256) float32 mask prompts, the `mask_input` the
+        rbox driver builds per box with OpenCV on the host (main_sam_rbox_mask_instance.py:125-141,159-164).
+        `check` synchronises once to verify that every vertex was inside the image (outside vertices are not supported)."""
+        p = self._dev(polys, torch.float32).reshape(-1, 4, 2)
+        B, (H, W) = p.shape[0], (int(image_hw[0]), int(image_hw[1]))
+        out = torch.empty((B, 1, 256, 256), dtype=torch.float32, device=self.device)
+        status = torch.empty((1,), dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            self._check(self._lib.samrs_rbox_mask_prompts(self._h, p.data_ptr(), B, H, W, out.data_ptr(), status.data_ptr(),
+                                                          _stream(self.device)), "rbox_mask_prompts")
+        if check and B > 0 and int(status.item()) != 0:
+            raise ValueError("rbox_mask_prompts: a polygon vertex lies outside the image (after truncation to integers)")
+        return out
+
     def paint_masks(self, masks: torch.Tensor, class_ids: torch.Tensor, label_map: torch.Tensor) -> torch.Tensor:
         """In-place painter reduce of (B,[1,]H,W) bool masks into an (H,W) uint8 label map: the general-size companion of
         `semantic_reduce` (tiles whose original size is not 1024 x 1024)."""
@@ -292,6 +309,10 @@ class Engine:
     def set_graphs(self, enable: bool) -> None:
         """CUDA-graph replay of the encode / decode bodies (default on); off = every kernel is launched directly."""
         self._check(self._lib.samrs_set_graphs(self._h, int(bool(enable))), "set_graphs")
+
+    def set_pdl(self, enable: bool) -> None:
+        """Programmatic dependent launch of the GEMM / attention / LayerNorm kernels (default on)."""
+        self._check(self._lib.samrs_set_pdl(self._h, int(bool(enable))), "set_pdl")
 
     def launch_count(self) -> int:
         c = ctypes.c_int64(0)
