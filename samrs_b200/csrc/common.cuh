@@ -317,6 +317,6 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
                  uint64_t pitch2_bytes, uint32_t b0, uint32_t b1, uint32_t b2);
 // output tensor map for the GEMM epilogue's TMA stores: [batch][M][N] fp16 (no swizzle) or fp32 (128-byte swizzle), box 32x32
 int make_tmap_out(CUtensorMap* out, const void* base, bool half, uint64_t N, uint64_t M, uint64_t batch, uint64_t ld_elems,
-                  uint64_t batch_stride_elems);
+                  uint64_t batch_stride_elems, uint32_t box_cols = 32);
 
 }  // namespace samrs

@@ -81,16 +81,16 @@ int make_tmap_3d(CUtensorMap* out, const void* base, uint64_t d0, uint64_t d1, u
 }
 
 int make_tmap_out(CUtensorMap* out, const void* base, bool half, uint64_t N, uint64_t M, uint64_t batch, uint64_t ld_elems,
-                  uint64_t batch_stride_elems) {
+                  uint64_t batch_stride_elems, uint32_t box_cols) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) SAMRS_FAIL("cuTensorMapEncodeTiled unavailable");
   const uint64_t es = half ? 2 : 4;
   cuuint64_t dims[3] = {N, M, batch};
   cuuint64_t strides[2] = {ld_elems * es, (batch > 1 ? batch_stride_elems : ld_elems * M) * es};
-  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t box[3] = {box_cols, 32, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUresult r = enc(out, half ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void*>(base), dims,
-                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, half ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, (half || box_cols != 32) ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) SAMRS_FAIL("cuTensorMapEncodeTiled(out) failed");
   return 0;
@@ -178,10 +178,10 @@ static int launch_gemm_mc_inst(const CUtensorMap& tA, const CUtensorMap& tB, con
 #endif
 
 template <int BN, bool OH, int ACT>
-static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
+static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tC16, const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   SAMRS_TRY(opt_in_smem(gemm_tc2_kernel<BN, OH, ACT>, Cfg::kSmemBytes));
-  SAMRS_CUDA_OK(launch_pdl(gemm_tc2_kernel<BN, OH, ACT>, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, tA, tB, tC, p));
+  SAMRS_CUDA_OK(launch_pdl(gemm_tc2_kernel<BN, OH, ACT>, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, tA, tB, tC, tC16, p));
   count_launch();
   return 0;
 }
@@ -246,7 +246,12 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   if (mcast && (((p.M + 127) / 128) % 2 != 0 || (num_sms & 1) || a_map_rank3)) mcast = false;
   SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t((pair || mcast) ? bn / 2 : bn)));
   CUtensorMap tC;
-  SAMRS_TRY(make_tmap_out(&tC, p.out, out_half, uint64_t(p.N), uint64_t(p.M), uint64_t(p.batch), uint64_t(p.ldc), uint64_t(p.out_batch_stride)));
+  SAMRS_TRY(make_tmap_out(&tC, p.out, out_half, uint64_t(p.N), uint64_t(p.M), uint64_t(p.batch), uint64_t(p.ldc), uint64_t(p.out_batch_stride), 32));
+  CUtensorMap tC16 = tC;
+  if (bn % 32 != 0) {
+    if (!pair || out_half || bn % 32 != 16) SAMRS_FAIL("gemm: tiles that are not a multiple of 32 wide exist for the fp32 CTA-pair kernel only");
+    SAMRS_TRY(make_tmap_out(&tC16, p.out, false, uint64_t(p.N), uint64_t(p.M), uint64_t(p.batch), uint64_t(p.ldc), uint64_t(p.out_batch_stride), 16));
+  }
   if (p.res != nullptr && (p.ldr % 4 != 0)) SAMRS_FAIL("gemm: residual leading dimension must be a multiple of 4");
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
   if (pair) {
@@ -254,11 +259,15 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
     const int grid2 = 2 * (tiles < pairs ? tiles : pairs);
 #define SAMRS_GEMM2_CASE(BN_)                                                                       \
   if (bn == BN_) {                                                                                  \
-    if (out_half && act == 0) return launch_gemm2_inst<BN_, true, 0>(tA, tB, tC, p, grid2, stream);     \
-    if (out_half && act == 1) return launch_gemm2_inst<BN_, true, 1>(tA, tB, tC, p, grid2, stream);     \
-    if (!out_half && act == 0) return launch_gemm2_inst<BN_, false, 0>(tA, tB, tC, p, grid2, stream);   \
+    if (out_half && act == 0) return launch_gemm2_inst<BN_, true, 0>(tA, tB, tC, tC16, p, grid2, stream);     \
+    if (out_half && act == 1) return launch_gemm2_inst<BN_, true, 1>(tA, tB, tC, tC16, p, grid2, stream);     \
+    if (!out_half && act == 0) return launch_gemm2_inst<BN_, false, 0>(tA, tB, tC, tC16, p, grid2, stream);   \
     SAMRS_FAIL("gemm: unsupported epilogue");                                                       \
   }
+    if (bn == 144) {
+      if (out_half || act != 0) SAMRS_FAIL("gemm: the 144-wide pair tile has the fp32 epilogue only");
+      return launch_gemm2_inst<144, false, 0>(tA, tB, tC, tC16, p, grid2, stream);
+    }
     SAMRS_GEMM2_CASE(256)
     SAMRS_GEMM2_CASE(224)
     SAMRS_GEMM2_CASE(160)

@@ -97,8 +97,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
 template <int BN, int ACT>
 __device__ __forceinline__ void gemm_epilogue_warp_half(const GemmParams& p, const CUtensorMap* tmC, uint32_t t_addr, int row0, int n0,
                                                         int bt, float oscale, uint8_t* stage, uint32_t& nstaged, int lane,
-                                                        const float (&bias_r)[BN / 32], int chunk_begin, int chunk_end) {
-  constexpr int NCH = BN / 32;
+                                                        const float (&bias_r)[(BN + 31) / 32], int chunk_begin, int chunk_end) {
+  static_assert(BN % 32 == 0, "fp16-output tiles are whole 32-column chunks");
+  constexpr int NCH = (BN + 31) / 32;
   auto convert = [&](const uint32_t (&v)[32], float bias_c, uint8_t* buf) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -148,7 +149,7 @@ __device__ __forceinline__ void gemm_epilogue_warp_half(const GemmParams& p, con
 // materialised: each 32-column chunk is one output pixel of the row's 2 x 2 block, written as one float per mask.
 template <int BN>
 __device__ __forceinline__ void gemm_epilogue_warp_upscale2(const GemmParams& p, uint32_t t_addr, int row0, float oscale, int lane,
-                                                            const float (&bias_r)[BN / 32], int chunk_begin, int chunk_end) {
+                                                            const float (&bias_r)[(BN + 31) / 32], int chunk_begin, int chunk_end) {
   static_assert(BN == 128, "the up-scaling epilogue expects the four 32-channel groups in one tile");
   const int m = row0 + lane;
   const bool ok = m < p.M;
@@ -157,7 +158,7 @@ __device__ __forceinline__ void gemm_epilogue_warp_upscale2(const GemmParams& p,
   const int Y = 2 * (token >> 6) + (d1 >> 1), X = 2 * (token & 63) + (d1 & 1);      // position in the 128 x 128 grid
   const int bw = __shfl_sync(0xffffffffu, b, 0);                                   // 16384 rows per prompt: uniform in a tile
 #pragma unroll
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = 0; c < (BN + 31) / 32; ++c) {
     if (c < chunk_begin || c >= chunk_end) continue;
     uint32_t v[32];
     tmem_ld32(t_addr + uint32_t(c * 32), v);
@@ -189,9 +190,9 @@ __device__ __forceinline__ void gemm_epilogue_warp_upscale2(const GemmParams& p,
 // left are the bias (prefetched before the accumulator is ready) and the optional residual (prefetched one chunk
 // ahead), and the stores never stall the warp.
 template <int BN, bool OUT_HALF, int ACT>
-__device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CUtensorMap* tmC, uint32_t t_addr, int row0, int n0,
+__device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmC16, uint32_t t_addr, int row0, int n0,
                                                    int bt, float oscale, uint8_t* stage /*8 KiB, 1024-B aligned*/, uint32_t& nstaged,
-                                                   int lane, const float (&bias_r)[BN / 32], int chunk_begin, int chunk_end) {
+                                                   int lane, const float (&bias_r)[(BN + 31) / 32], int chunk_begin, int chunk_end) {
   if constexpr (OUT_HALF) {
     gemm_epilogue_warp_half<BN, ACT>(p, tmC, t_addr, row0, n0, bt, oscale, stage, nstaged, lane, bias_r, chunk_begin, chunk_end);
     return;
@@ -200,7 +201,7 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
     gemm_epilogue_warp_upscale2<BN>(p, t_addr, row0, oscale, lane, bias_r, chunk_begin, chunk_end);
     return;
   }
-  constexpr int NCH = BN / 32;
+  constexpr int NCH = (BN + 31) / 32;
   const int row = row0 + lane;
   const float* res_row = nullptr;
   if (p.res != nullptr && row < p.M) res_row = p.res + size_t(p.res_mod > 0 ? row % p.res_mod : row) * p.ldr + n0;
@@ -216,6 +217,33 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   for (int c = 0; c < NCH; ++c) {
     if (c < chunk_begin || c >= chunk_end) continue;
     if (n0 + c * 32 >= p.N) break;
+    if (BN % 32 != 0 && c == NCH - 1) {
+      // 16-column tail of a tile whose width is not a multiple of 32 (BN = 144): same steps through a 16 x 32 box
+      uint32_t v[16];
+      tmem_ld16(t_addr + uint32_t(c * 32), v);
+      tc_wait_ld();
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), oscale, __shfl_sync(0xffffffffu, bias_r[c], j));
+      if (p.res != nullptr) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { f[4 * j] += rn[j].x; f[4 * j + 1] += rn[j].y; f[4 * j + 2] += rn[j].z; f[4 * j + 3] += rn[j].w; }
+      }
+      uint8_t* buf = stage + (nstaged % 2) * (GEMM_EPI_WARP_SMEM / 2);
+      ++nstaged;
+      if (elect_one()) tma_store_wait_read<1>();
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) *reinterpret_cast<float4*>(buf + lane * 64 + j * 16) = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (elect_one()) {
+        if (p.accumulate) tma_reduce_add_3d(tmC16, buf, n0 + c * 32, row0, bt);
+        else tma_store_3d(tmC16, buf, n0 + c * 32, row0, bt);
+        tma_store_commit();
+      }
+      continue;
+    }
     const bool trc = kGemmExp && (p.dbg != nullptr) && (threadIdx.x >> 5) == 4 && lane == 0 && nstaged < 32;
     const int tslot = 2048 + int(nstaged) * 8;
     if (trc) gemm_dbg(p, tslot + 0);
@@ -279,9 +307,9 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
 
 // bias of the tile's columns, one value per lane and 32-column chunk; loaded before the accumulator is ready
 template <int BN>
-__device__ __forceinline__ void gemm_load_bias(const GemmParams& p, int n0, int lane, float (&bias_r)[BN / 32]) {
+__device__ __forceinline__ void gemm_load_bias(const GemmParams& p, int n0, int lane, float (&bias_r)[(BN + 31) / 32]) {
 #pragma unroll
-  for (int c = 0; c < BN / 32; ++c) {
+  for (int c = 0; c < (BN + 31) / 32; ++c) {
     const int col = n0 + c * 32 + lane;
     bias_r[c] = (p.bias != nullptr && col < p.N) ? __ldg(p.bias + col) : 0.f;
   }
@@ -294,6 +322,7 @@ template <int BN, bool OUT_HALF, int ACT, int CM = 1>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+  static_assert(BN % 32 == 0, "the 1-CTA kernel takes whole 32-column chunks");
   using Cfg = GemmCfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -423,7 +452,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const float oscale = (p.out_scale != 0.f) ? p.out_scale : 1.0f;
     uint8_t* my_stage = epi_stage + (warp - 4) * GEMM_EPI_WARP_SMEM;
     uint32_t nstaged = 0;
-    constexpr int NCH = BN / 32, SPLIT = OUT_HALF ? ((NCH + 1) / 4) * 2 : (NCH + 1) / 2;   // fp16: whole chunk pairs per group
+    constexpr int NCH = (BN + 31) / 32, SPLIT = OUT_HALF ? ((NCH + 1) / 4) * 2 : (NCH + 1) / 2;   // fp16: whole chunk pairs per group
     const int cb = (warp < 8) ? 0 : SPLIT, ce = (warp < 8) ? SPLIT : NCH;
     int as = 0, eti = 0;
     uint32_t aphase = 0;
@@ -432,14 +461,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int bt = t / tiles_mn, tt = t % tiles_mn;
       const int m0 = (tt % p.tiles_m) * GEMM_BM;
       const int n0 = (tt / p.tiles_m) * BN;
-      float bias_r[BN / 32];
+      float bias_r[(BN + 31) / 32];
       gemm_load_bias<BN>(p, n0, lane, bias_r);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       if (warp == 4 && lane == 0) gemm_dbg(p, 16 + eti * 64 + 61);
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
       if (!kGemmExp || !(p.dbg_mode & 4))
-        gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, bt, oscale, my_stage, nstaged, lane, bias_r, cb, ce);
+        gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, &tmC, t_addr, m0 + q * 32, n0, bt, oscale, my_stage, nstaged, lane, bias_r, cb, ce);
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       __syncwarp();

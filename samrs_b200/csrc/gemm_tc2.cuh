@@ -28,7 +28,8 @@ struct Gemm2Cfg {
 template <int BN, bool OUT_HALF, int ACT>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                const __grid_constant__ CUtensorMap tmC, const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmC16 /*16-column tail box (BN % 32 == 16)*/,
+                const GemmParams p) {
   using Cfg = Gemm2Cfg<BN>;
   constexpr int S = Cfg::kStages;
   extern __shared__ uint8_t smem_raw[];
@@ -141,20 +142,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
     const float oscale = (p.out_scale != 0.f) ? p.out_scale : 1.0f;
     uint8_t* my_stage = epi_stage + (warp - 4) * GEMM_EPI_WARP_SMEM;
     uint32_t nstaged = 0;
-    constexpr int NCH = BN / 32, SPLIT = OUT_HALF ? ((NCH + 1) / 4) * 2 : (NCH + 1) / 2;   // fp16: whole chunk pairs per group
+    constexpr int NCH = (BN + 31) / 32, SPLIT = OUT_HALF ? ((NCH + 1) / 4) * 2 : (NCH + 1) / 2;   // fp16: whole chunk pairs per group
     const int cb = (warp < 8) ? 0 : SPLIT, ce = (warp < 8) ? SPLIT : NCH;
     int as = 0, eti = 0;
     uint32_t aphase = 0;
     for (int t = pair; t < num_tiles; t += num_pairs) {
       const int m0 = (t % p.tiles_m) * 256 + int(rank) * GEMM_BM;
       const int n0 = (t / p.tiles_m) * BN;
-      float bias_r[BN / 32];
+      float bias_r[(BN + 31) / 32];
       gemm_load_bias<BN>(p, n0, lane, bias_r);
       mbar_wait(&tfull[as], aphase);
       tc_fence_after();
       if (warp == 4 && lane == 0) gemm_dbg(p, 16 + eti * 64 + 61);
       const uint32_t t_addr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * BN);
-      gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, t_addr, m0 + q * 32, n0, 0, oscale, my_stage, nstaged, lane, bias_r, cb, ce);
+      gemm_epilogue_warp<BN, OUT_HALF, ACT>(p, &tmC, &tmC16, t_addr, m0 + q * 32, n0, 0, oscale, my_stage, nstaged, lane, bias_r, cb, ce);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty[as], 0));

@@ -32,6 +32,8 @@ def _rand(shape, seed, scale=1.0, dtype=torch.float16):
     # CTA-pair (cta_group::2) kernel: force_bn = 1000 + N tile
     (256, 256, 64, 1256), (512, 256, 256, 1128), (4096, 3840, 1280, 1256), (4096, 1280, 5120, 1160),
     (4096, 1280, 1280, 1128), (700, 520, 200, 1256), (131072, 384, 768, 0),
+    # 144-wide pair tiles (16-column tail chunk through its own TMA box): N = 8 x 144 + 128, ragged N, tiny
+    (4096, 1280, 1280, 1144), (4096, 1280, 5120, 1144), (700, 520, 200, 1144), (256, 144, 64, 1144),
 ])
 def test_gemm_fp32_out_bias_residual(eng64, M, N, K, bn):
     A, B = _rand((M, K), 1), _rand((N, K), 2, 1.0 / math.sqrt(K))
@@ -45,7 +47,8 @@ def test_gemm_fp32_out_bias_residual(eng64, M, N, K, bn):
     assert err < 2e-3, f"max err {err}"
 
 
-@pytest.mark.parametrize("M,N,K,bn", [(4096, 1280, 1280, 0), (4096, 1280, 5120, 1160), (300, 200, 192, 160), (4096, 1280, 1280, 1256)])
+@pytest.mark.parametrize("M,N,K,bn", [(4096, 1280, 1280, 0), (4096, 1280, 5120, 1160), (300, 200, 192, 160), (4096, 1280, 1280, 1256),
+                                         (4096, 1280, 5120, 1144), (512, 304, 128, 1144)])
 def test_gemm_inplace_residual_reduce_add(eng64, M, N, K, bn):
     """x += A B^T + bias with x both residual and output: the epilogue issues TMA reduce-add stores."""
     A, B = _rand((M, K), 31), _rand((N, K), 32, 1.0 / math.sqrt(K))

@@ -26,6 +26,8 @@ for name, (M, N, K, half, gelu) in shapes.items():
     res[f"{name}/cublas"] = (round(us, 1), round(2.0 * M * N * K / us / 1e6, 1))
     print(f"{name:11s} cuBLAS   : {us:7.1f} us  {2.0*M*N*K/us/1e6:7.1f} TFLOP/s", flush=True)
     for c in cfgs:
+        if half and c % 1000 % 32 != 0:
+            continue                        # tiles that are not a multiple of 32 wide have the fp32 epilogue only
         for _ in range(3):
             eng.test_gemm(A, B, out_half=half, bias=bias, res=r, gelu=gelu, force_bn=c)
         torch.cuda.synchronize()
