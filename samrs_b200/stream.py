@@ -184,7 +184,9 @@ def run(predictor, jobs: Iterable, save_dir: str = None, mapping=None, categorie
       finisher thread waits for the slot's event, builds the instance records and hands the tile to
       writer threads  `writers.save_tile` (gray / color PNG + pickle), the reference's on-disk contract
     Slots are recycled in order, so at most `depth` tiles are in flight and the GPU thread never waits for a writer
-    unless the writers fall `depth` tiles behind.  Returns counters (`tiles`, `masks`, `seconds`)."""
+    unless the writers fall `depth` tiles behind.  Returns counters: `tiles`, `masks`, `seconds` (wall clock until the last
+    file is written), `seconds_before_writers_drain` (until every tile's outputs are on the host) and `writer_cpu_seconds`
+    (time spent inside PNG / pickle encoding, summed over the writer threads)."""
     import queue
     import threading
     import time
@@ -251,10 +253,21 @@ def run(predictor, jobs: Iterable, save_dir: str = None, mapping=None, categorie
                 if on_tile is not None:
                     on_tile(job, label_map, records)
                 if save_dir is not None:
-                    pool.submit(writers.save_tile, save_dir, job.name, label_map, mapping, records)
+                    pool.submit(timed_save, save_dir, job.name, label_map, mapping, records)
             except BaseException as ex:
                 errors.append(ex)
                 free_slots.put(slot)
+
+    writer_cpu = [0.0]
+
+    def timed_save(*a):
+        t = time.time()
+        try:
+            writers.save_tile(*a)
+        except BaseException as ex:
+            errors.append(ex)
+        with lock:
+            writer_cpu[0] += time.time() - t
 
     loaders = [threading.Thread(target=loader, daemon=True) for _ in range(max(1, loader_threads))]
     pool = ThreadPoolExecutor(max_workers=max(1, writer_threads))
@@ -290,7 +303,9 @@ def run(predictor, jobs: Iterable, save_dir: str = None, mapping=None, categorie
     finally:
         done_q.put(None)
         fin.join()
+        t_payload = time.time() - t0                         # every tile's label map and records are on the host
         pool.shutdown(wait=True)
     if errors:
         raise errors[0]
-    return {"tiles": tiles, "masks": masks, "seconds": time.time() - t0}
+    return {"tiles": tiles, "masks": masks, "seconds": time.time() - t0, "seconds_before_writers_drain": t_payload,
+            "writer_cpu_seconds": writer_cpu[0]}
