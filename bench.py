@@ -277,8 +277,6 @@ class Rig:
             e_.load_state_dict(sd)
             if os.environ.get("SAMRS_PDL") == "0":         # A/B switches (defaults: CUDA graphs and PDL on)
                 e_.set_pdl(False)
-            if os.environ.get("SAMRS_FUSE_LN") == "0":
-                e_.set_fused_layernorm(False)
             if os.environ.get("SAMRS_GRAPHS") == "0":
                 e_.set_graphs(False)
             self.engines.append(e_)

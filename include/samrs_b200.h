@@ -115,12 +115,6 @@ int samrs_set_graphs(void* engine, int enable);
  * stream order for A/B measurements. */
 int samrs_set_pdl(void* engine, int enable);
 
-/* LayerNorm as the tail of the residual GEMMs (default on for ViT-H on a 148-SM device): proj and lin2 are launched
- * cooperatively, and after a grid barrier their CTAs normalise the residual stream they have just updated into the next
- * GEMM's fp16 operand (image_encoder.py:167,181 norm1 / norm2).  enable = 0 launches every LayerNorm as its own kernel;
- * both placements run the same per-row arithmetic and give identical bits. */
-int samrs_set_fused_layernorm(void* engine, int enable);
-
 /* kernels launched by this engine since creation (bench.py's gpu_launches). */
 int samrs_launch_count(void* engine, int64_t* count_out);
 

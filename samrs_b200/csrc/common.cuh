@@ -70,77 +70,6 @@ __device__ __forceinline__ bool elect_one() {
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
-// ---------------------------------------------------------------- grid-wide barrier (cooperative launches only)
-// bar[0] = arrival count, bar[1] = generation.  Every CTA reads the generation BEFORE it arrives; the last arriver resets
-// the count and bumps the generation, so the same two words serve every launch (and every graph replay) of an engine.
-// Requires all CTAs of the grid to be co-resident: the kernel must be launched with cudaLaunchAttributeCooperative.
-__device__ __forceinline__ void grid_barrier(unsigned int* bar, unsigned int nblocks) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    volatile unsigned int* gen = bar + 1;
-    const unsigned int my_gen = *gen;
-    __threadfence();
-    const unsigned int old = atomicAdd(bar, 1u);
-    if (old == nblocks - 1) {
-      atomicExch(bar, 0u);
-      __threadfence();
-      atomicAdd(bar + 1, 1u);
-    } else {
-      while (*gen == my_gen) __nanosleep(32);
-    }
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// ---------------------------------------------------------------- LayerNorm of one row by one warp (fp32 in, fp16 out)
-// Shared by the stand-alone streaming kernel (simt.cuh) and the tail of the residual GEMMs (gemm_tc2.cuh), so that both
-// paths produce identical bits: two-pass mean / biased variance in registers, same summation order.
-template <int MAXV /* float4 per lane: C == 128 * MAXV */, bool L2_ONLY>
-__device__ __forceinline__ void ln_row_load(const float* __restrict__ row, int lane, float4 (&v)[MAXV]) {
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const float4* src = reinterpret_cast<const float4*>(row) + lane + 32 * i;
-    v[i] = L2_ONLY ? __ldcg(src) : *src;
-  }
-}
-template <int MAXV>
-__device__ __forceinline__ void ln_row_finish(const float4 (&v)[MAXV], const float* __restrict__ gamma, const float* __restrict__ beta,
-                                              float eps, __half* __restrict__ out_row, int lane) {
-  constexpr float Cf = float(128 * MAXV);
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / Cf;
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
-    q += (a * a + b * b) + (c * c + d * d);
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / Cf + eps);
-  uint2* dst = reinterpret_cast<uint2*>(out_row);
-#pragma unroll
-  for (int i = 0; i < MAXV; ++i) {
-    const int k = lane + 32 * i;
-    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + k);
-    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + k);
-    const float y0 = (v[i].x - mean) * rstd * g.x + b.x;
-    const float y1 = (v[i].y - mean) * rstd * g.y + b.y;
-    const float y2 = (v[i].z - mean) * rstd * g.z + b.z;
-    const float y3 = (v[i].w - mean) * rstd * g.w + b.w;
-    __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
-    uint2 pk;
-    pk.x = *reinterpret_cast<uint32_t*>(&h0);
-    pk.y = *reinterpret_cast<uint32_t*>(&h1);
-    dst[k] = pk;
-  }
-}
-
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -181,18 +181,6 @@ template <int BN, bool OH, int ACT>
 static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tC16, const GemmParams& p, int grid, cudaStream_t st) {
   using Cfg = Gemm2Cfg<BN>;
   SAMRS_TRY(opt_in_smem(gemm_tc2_kernel<BN, OH, ACT>, Cfg::kSmemBytes));
-  if (p.ln_out != nullptr) {
-    // fused LayerNorm tail: the grid barrier inside needs every CTA resident -> cooperative launch (no PDL overlap)
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::kSmemBytes; cfg.stream = st;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeCooperative;
-    at[0].val.cooperative = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    SAMRS_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_tc2_kernel<BN, OH, ACT>, tA, tB, tC, tC16, p));
-    count_launch();
-    return 0;
-  }
   SAMRS_CUDA_OK(launch_pdl(gemm_tc2_kernel<BN, OH, ACT>, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, tA, tB, tC, tC16, p));
   count_launch();
   return 0;
@@ -266,8 +254,6 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   }
   if (p.res != nullptr && (p.ldr % 4 != 0)) SAMRS_FAIL("gemm: residual leading dimension must be a multiple of 4");
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
-  if (p.ln_out != nullptr && !(pair && !out_half && act == 0 && tiles >= num_sms / 2))
-    SAMRS_FAIL("gemm: the fused LayerNorm tail needs the fp32 CTA-pair kernel on a full grid");
   if (pair) {
     const int pairs = num_sms / 2;
     const int grid2 = 2 * (tiles < pairs ? tiles : pairs);
@@ -373,8 +359,6 @@ struct Engine {
   // later calls replay the instantiated graph into the caller's stream.  Kernels that touch caller-owned pointers (image
   // in, features / logits / IoU out, prompts) stay outside the graphs.  Profiling (per-launch events) runs eagerly.
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int launches = 0; int eager_runs = 0; };
-  bool fuse_ln = true;                 // LayerNorm as the tail of the residual GEMMs (cooperative launch); off -> separate kernels
-  unsigned int* ln_bar = nullptr;      // grid-barrier words of the fused LayerNorm
   bool graphs_enabled = true;
   cudaStream_t cap_stream = nullptr;
   GraphEntry enc_graph;
@@ -893,8 +877,6 @@ static int alloc_activations(Engine* e) {
   SAMRS_TRY(e->alloc(&e->K0, T * 128));
   SAMRS_TRY(e->alloc(&e->V0, T * 128));
   SAMRS_TRY(e->alloc(&e->Qi0, T * 128));
-  SAMRS_TRY(e->alloc(&e->ln_bar, 64));
-  SAMRS_CUDA_OK(cudaMemset(e->ln_bar, 0, 64 * sizeof(unsigned int)));
   e->ctx.splitk_ws_floats = size_t(8) * 1024 * 2048;
   SAMRS_TRY(e->alloc(&e->ctx.splitk_ws, e->ctx.splitk_ws_floats));
   return 0;
@@ -946,15 +928,9 @@ static int ensure_mask_scratch(Engine* e, int B) {
 }
 
 // ------------------------------------------------------------------ encoder
-struct LnTail { const float* gamma; const float* beta; __half* out; int ld_out; float eps; };
-
 static int gemm_enc(Engine* e, cudaStream_t st, const __half* A, int lda, const __half* W, int M, int N, int K, void* out, int ldc,
-                    bool out_half, const float* bias, const float* res, int ldr, int res_mod, int act, int accumulate = 0,
-                    const LnTail* ln = nullptr) {
+                    bool out_half, const float* bias, const float* res, int ldr, int res_mod, int act, int accumulate = 0) {
   GemmParams p;
-  if (ln != nullptr) {
-    p.ln_gamma = ln->gamma; p.ln_beta = ln->beta; p.ln_out = ln->out; p.ln_ld_out = ln->ld_out; p.ln_eps = ln->eps; p.ln_bar = e->ln_bar;
-  }
   p.M = M; p.N = N; p.K = K;
   p.out = out; p.ldc = ldc;
   p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
@@ -982,24 +958,16 @@ static int encode_body(Engine* e, cudaStream_t st) {
   const int D = e->D, T = 4096;
   // patch embedding + absolute position embedding (image_encoder.py:107-109)
   SAMRS_TRY(gemm_enc(e, st, e->a_pe, 768, e->w_patch, T, D, 768, e->x, D, false, e->b_patch, e->pos_embed, D, 0, 0));
-  // LayerNorm placement: with `fuse_ln` (ViT-H on a full 148-SM grid, where proj / lin2 are CTA-pair GEMMs) norm2 rides as the tail of the proj GEMM
-  // and norm1 of block i+1 as the tail of block i's lin2 GEMM, both after a grid barrier inside the persistent kernel
-  // (gemm_tc2.cuh); only the first norm1 is a kernel of its own.  Otherwise every LayerNorm is a separate launch.
-  // (Per-launch profiling keeps the LayerNorms separate so that the GEMM category times the GEMM alone; same bits.)
-  const bool fuse = e->fuse_ln && T == 4096 && D == 1280 && e->num_sms == 148 && !(t_ctx && t_ctx->prof.on);
   for (int i = 0; i < e->depth; ++i) {
     const BlockWeights& b = e->blocks[i];
-    if (i == 0 || !fuse) { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln1w, b.ln1b, 1e-6f, e->xn, D, T, D))); }
+    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln1w, b.ln1b, 1e-6f, e->xn, D, T, D))); }
     SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.wqkv, T, 3 * D, D, e->qkv, 3 * D, true, b.bqkv_eff, nullptr, 0, 0, 0));
     SAMRS_TRY(encoder_attention(e, st, e->qkv, b.reltab, b.global, e->attn_o));
     // proj / lin2 update the fp32 residual stream in place: x += A W^T + b through TMA reduce-add stores
-    const LnTail ln2{b.ln2w, b.ln2b, e->xn, D, 1e-6f};
-    SAMRS_TRY(gemm_enc(e, st, e->attn_o, D, b.wproj, T, D, D, e->x, D, false, b.bproj_eff, nullptr, 0, 0, 0, 1, fuse ? &ln2 : nullptr));
-    if (!fuse) { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln2w, b.ln2b, 1e-6f, e->xn, D, T, D))); }
+    SAMRS_TRY(gemm_enc(e, st, e->attn_o, D, b.wproj, T, D, D, e->x, D, false, b.bproj_eff, nullptr, 0, 0, 0, 1));
+    { ProfScope ps(PC_LN, st); SAMRS_TRY((ln_rows<__half, 0>(st, e->x, D, b.ln2w, b.ln2b, 1e-6f, e->xn, D, T, D))); }
     SAMRS_TRY(gemm_enc(e, st, e->xn, D, b.w1, T, 4 * D, D, e->hid, 4 * D, true, b.b1, nullptr, 0, 0, 1));
-    const bool next = fuse && i + 1 < e->depth;
-    const LnTail ln1{next ? e->blocks[i + 1].ln1w : nullptr, next ? e->blocks[i + 1].ln1b : nullptr, e->xn, D, 1e-6f};
-    SAMRS_TRY(gemm_enc(e, st, e->hid, 4 * D, b.w2, T, D, 4 * D, e->x, D, false, b.b2, nullptr, 0, 0, 0, 1, next ? &ln1 : nullptr));
+    SAMRS_TRY(gemm_enc(e, st, e->hid, 4 * D, b.w2, T, D, 4 * D, e->x, D, false, b.b2, nullptr, 0, 0, 0, 1));
   }
   // neck (image_encoder.py:88-104)
   cast_f32_f16_kernel<<<unsigned((size_t(T) * D / 4 + 255) / 256), 256, 0, st>>>(e->x, e->x16, size_t(T) * D / 4);
@@ -1611,16 +1579,6 @@ int samrs_set_pdl(void* engine, int enable) {
   cudaDeviceSynchronize();
   e->ctx.pdl = enable != 0;
   e->drop_graphs();                                  // captured launches carry the attribute
-  return 0;
-}
-
-int samrs_set_fused_layernorm(void* engine, int enable) {
-  Engine* e = static_cast<Engine*>(engine);
-  if (!e) return 1;
-  cudaSetDevice(e->device);
-  cudaDeviceSynchronize();
-  e->fuse_ln = enable != 0;
-  e->drop_graphs();
   return 0;
 }
 

@@ -33,14 +33,6 @@ struct GemmParams {
   int accumulate;       // fp32 output only: out += result (TMA reduce-add) instead of out = result
   int dbg_mode;         // tools only (results are garbage): bit0 skip TMA loads, bit1 skip MMAs, bit2 skip the epilogue
   // ACT == 3 (mask decoder, second up-scaling stage fused with the hyper-network product; see gemm_epilogue_warp_upscale2):
-  // fused LayerNorm tail of the residual GEMMs (gemm_tc2_kernel, cooperative launch): once every CTA's reduce-add stores have
-  // landed (grid barrier), the CTAs normalise the rows of the updated residual stream into the next GEMM's fp16 operand
-  const float* ln_gamma = nullptr;
-  const float* ln_beta = nullptr;
-  __half* ln_out = nullptr;       // [M][ln_ld_out] fp16; nullptr = no fused LayerNorm
-  int ln_ld_out = 0;
-  float ln_eps = 0.f;
-  unsigned int* ln_bar = nullptr; // two words of the engine: arrival count, generation
   const float* hyper = nullptr;   // [B][hyper_nm][32]
   float* low = nullptr;           // [B][hyper_nm][256][256] low-res mask logits
   int hyper_nm = 0;

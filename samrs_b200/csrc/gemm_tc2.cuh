@@ -13,8 +13,6 @@
 //   empty[s]  : one per CTA; tcgen05.commit.multicast from the leader releases the slot in both CTAs.
 //   tfull[a]  : one per CTA (multicast commit); tempty[a]: leader's, 16 arrivals (8 epilogue warps x 2 CTAs).
 #pragma once
-#include <type_traits>
-
 #include "gemm_tc.cuh"
 
 namespace samrs {
@@ -166,10 +164,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
       as ^= 1;
       if (as == 0) aphase ^= 1;
     }
-    if (elect_one()) {
-      tma_store_wait_all();                         // this warp's stores / reduce-adds have been performed
-      asm volatile("fence.proxy.async;" ::: "memory");
-    }
+    if (elect_one()) tma_store_wait_all();
   }
 
   tc_fence_before();
@@ -179,28 +174,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc_pair<Cfg::kTmemCols>(tmem_base);
-  }
-  if constexpr (!OUT_HALF && ACT == 0) {
-    if (p.ln_out != nullptr) {
-      // LayerNorm of the residual stream this GEMM has just updated in place, for the next GEMM's A operand.  The rows are
-      // spread over the whole grid (row = CTA, CTA + grid, ...; one warp per row), which needs every CTA's reduce-adds: the
-      // epilogue warps above waited for theirs, the grid barrier publishes them.  Loads bypass L1 (the data was written
-      // through the L2 by the TMA unit); arithmetic = ln_rows_stream_kernel's.
-      grid_barrier(p.ln_bar, gridDim.x);
-      const float* xin = static_cast<const float*>(p.out);
-      const int nwarps = GEMM_THREADS / 32;
-      auto run = [&](auto maxv) {
-        constexpr int MAXV = decltype(maxv)::value;
-        for (int r = int(blockIdx.x) + warp * int(gridDim.x); r < p.M; r += nwarps * int(gridDim.x)) {
-          float4 v[MAXV];
-          ln_row_load<MAXV, true>(xin + size_t(r) * p.ldc, lane, v);
-          ln_row_finish<MAXV>(v, p.ln_gamma, p.ln_beta, p.ln_eps, p.ln_out + size_t(r) * p.ln_ld_out, lane);
-        }
-      };
-      if (p.N == 1280) run(std::integral_constant<int, 10>{});
-      else if (p.N == 1024) run(std::integral_constant<int, 8>{});
-      else if (p.N == 768) run(std::integral_constant<int, 6>{});
-    }
   }
 }
 

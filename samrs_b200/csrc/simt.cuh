@@ -53,13 +53,48 @@ __global__ void __launch_bounds__(64) ln_rows_stream_kernel(const float* __restr
   pdl_trigger();
   pdl_wait();
   if (row0 >= rows) return;
+  constexpr float Cf = float(128 * MAXV);
   float4 v[2][MAXV];
 #pragma unroll
-  for (int rr = 0; rr < 2; ++rr) ln_row_load<MAXV, false>(in + size_t(row0 + rr < rows ? row0 + rr : row0) * ld_in, lane, v[rr]);
+  for (int rr = 0; rr < 2; ++rr) {
+    const float4* src = reinterpret_cast<const float4*>(in + size_t(row0 + rr < rows ? row0 + rr : row0) * ld_in);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) v[rr][i] = src[lane + 32 * i];
+  }
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     if (row0 + rr >= rows) break;
-    ln_row_finish<MAXV>(v[rr], gamma, beta, eps, out + size_t(row0 + rr) * ld_out, lane);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) s += (v[rr][i].x + v[rr][i].y) + (v[rr][i].z + v[rr][i].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / Cf;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const float a = v[rr][i].x - mean, b = v[rr][i].y - mean, c = v[rr][i].z - mean, d = v[rr][i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / Cf + eps);
+    uint2* dst = reinterpret_cast<uint2*>(out + size_t(row0 + rr) * ld_out);
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int k = lane + 32 * i;
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + k);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + k);
+      const float y0 = (v[rr][i].x - mean) * rstd * g.x + b.x;
+      const float y1 = (v[rr][i].y - mean) * rstd * g.y + b.y;
+      const float y2 = (v[rr][i].z - mean) * rstd * g.z + b.z;
+      const float y3 = (v[rr][i].w - mean) * rstd * g.w + b.w;
+      __half2 h0 = __floats2half2_rn(y0, y1), h1 = __floats2half2_rn(y2, y3);
+      uint2 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0);
+      pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      dst[k] = pk;
+    }
   }
 }
 

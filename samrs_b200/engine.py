@@ -36,7 +36,6 @@ ABI = {
     "samrs_profile": (_i, [_vp, _i, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(_i), _i]),
     "samrs_set_graphs": (_i, [_vp, _i]),
     "samrs_set_pdl": (_i, [_vp, _i]),
-    "samrs_set_fused_layernorm": (_i, [_vp, _i]),
     "samrs_launch_count": (_i, [_vp, _i64p]),
     "samrs_last_error": (ctypes.c_char_p, [_vp]),
     "samrs_destroy": (None, [_vp]),
@@ -314,10 +313,6 @@ class Engine:
     def set_pdl(self, enable: bool) -> None:
         """Programmatic dependent launch of the GEMM / attention / LayerNorm kernels (default on)."""
         self._check(self._lib.samrs_set_pdl(self._h, int(bool(enable))), "set_pdl")
-
-    def set_fused_layernorm(self, enable: bool) -> None:
-        """LayerNorm as the tail of the proj / lin2 GEMMs (default on); off = one kernel per LayerNorm, same bits."""
-        self._check(self._lib.samrs_set_fused_layernorm(self._h, int(bool(enable))), "set_fused_layernorm")
 
     def launch_count(self) -> int:
         c = ctypes.c_int64(0)
