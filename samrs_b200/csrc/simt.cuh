@@ -780,33 +780,11 @@ __global__ void ln256_split_kernel(const float* __restrict__ in, const float* __
   }
 }
 
-// LayerNorm2d(64, eps 1e-6) + GELU of output_upscaling, in place on 64-channel groups laid out as
-// base[row * ld + off + g * 64 + c], g < 4 (the ConvT1 columns of the fused projection GEMM).  Half a warp per group.
-__global__ void ln64_gelu_grouped_kernel(float* __restrict__ base, int ld, int off, const float* __restrict__ gamma,
-                                         const float* __restrict__ beta, int rows) {
-  const int gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;       // (row, group)
-  const int l16 = threadIdx.x & 15;
-  if (gidx >= rows * 4) return;
-  float4* p = reinterpret_cast<float4*>(base + size_t(gidx >> 2) * ld + off + (gidx & 3) * 64) + l16;
-  const float4 a = *p;
-  float s = (a.x + a.y) + (a.z + a.w);
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s * (1.0f / 64.0f);
-  const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
-  float q = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = 1.0f / sqrtf(q * (1.0f / 64.0f) + 1e-6f);
-  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + l16);
-  const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + l16);
-  *p = make_float4(gelu_erf_f(g.x * (d0 * rstd) + be.x), gelu_erf_f(g.y * (d1 * rstd) + be.y),
-                   gelu_erf_f(g.z * (d2 * rstd) + be.z), gelu_erf_f(g.w * (d3 * rstd) + be.w));
-}
 
-// weight [N][K] fp32 -> split-fp16 [N][3K] = scale * [hi | hi | lo], matching activations stored [hi | lo | hi]
-// Same normalisation + GELU, but the result leaves as the 3-term split-fp16 A operand [hi | lo | hi] of the tensor-core
-// ConvTranspose2 GEMM: row (token * 4 + group) of out, 192 halves (precision recipe).
+// LayerNorm2d(64, eps 1e-6) + GELU of output_upscaling (SA/modeling/mask_decoder.py:54-57, common.py:31-43) on the 64-channel
+// groups base[row * ld + off + g * 64 + c], g < 4 (the ConvT1 columns of the fused projection GEMM); half a warp per group.
+// The result leaves as the 3-term split-fp16 A operand [hi | lo | hi] of the tensor-core ConvTranspose2 GEMM: row
+// (token * 4 + group) of out, 192 halves (precision recipe).
 __global__ void ln64_gelu_split_kernel(const float* __restrict__ base, int ld, int off, const float* __restrict__ gamma,
                                        const float* __restrict__ beta, int rows, __half* __restrict__ out /*[rows*4][192]*/) {
   const int gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;       // (row, group)
@@ -834,6 +812,7 @@ __global__ void ln64_gelu_split_kernel(const float* __restrict__ base, int ld, i
   *reinterpret_cast<uint2*>(o + 64) = *reinterpret_cast<const uint2*>(lo);
   *reinterpret_cast<uint2*>(o + 128) = *reinterpret_cast<const uint2*>(hi);
 }
+// weight [N][K] fp32 -> split-fp16 [N][3K] = scale * [hi | hi | lo], matching activations stored [hi | lo | hi]
 __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, float scale, __half* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * K) return;
@@ -846,64 +825,6 @@ __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, f
   o[2 * K + k] = lo;
 }
 
-// ------------------------------------------------------------------------------------------------
-// Second half of output_upscaling fused with the hypernetwork product
-// (SA/modeling/mask_decoder.py:53-59,154-167): for every 128x128 pixel u[64] (after ConvT1+LN2d+GELU)
-//   logit[m][2Y+dy][2X+dx] = sum_c hyper[b][m][c] * GELU(b2[c] + sum_k W2[k][c][dy][dx] u[k])
-// so the (B,32,256,256) upscaled embedding is never written.
-// One thread per (prompt, 128x128 pixel); W2 staged in smem as [dydx][c][k], all threads broadcast-read.
-// ------------------------------------------------------------------------------------------------
-template <int NM>
-__global__ void __launch_bounds__(128)
-upscale2_hyper_kernel(const float* __restrict__ u1 /*row (b,token) at u1 + (b*4096+token)*ld, 4 groups of 64*/, int ld,
-                      const float* __restrict__ w2r /*[4][32][64]*/,
-                      const float* __restrict__ b2, const float* __restrict__ hyper /*[B][NM][32]*/,
-                      float* __restrict__ low /*[B][NM][256][256]*/, int B) {
-  __shared__ __align__(16) float sw[4 * 32 * 64];
-  __shared__ float sb[32];
-  for (int i = threadIdx.x; i < 4 * 32 * 64; i += blockDim.x) sw[i] = w2r[i];
-  if (threadIdx.x < 32) sb[threadIdx.x] = b2[threadIdx.x];
-  __syncthreads();
-  const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (idx >= size_t(B) * 16384) return;
-  const int b = int(idx / 16384), rem = int(idx % 16384);
-  const int token = rem >> 2, d1 = rem & 3;
-  const int Y = 2 * (token >> 6) + (d1 >> 1), X = 2 * (token & 63) + (d1 & 1);     // 128x128 position
-  float u[64];
-  const float4* src = reinterpret_cast<const float4*>(u1 + (size_t(b) * 4096 + token) * ld + d1 * 64);
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const float4 t = src[i];
-    u[4 * i] = t.x; u[4 * i + 1] = t.y; u[4 * i + 2] = t.z; u[4 * i + 3] = t.w;
-  }
-  float hy[NM][32];
-#pragma unroll
-  for (int m = 0; m < NM; ++m)
-#pragma unroll
-    for (int c = 0; c < 32; ++c) hy[m][c] = __ldg(hyper + (size_t(b) * NM + m) * 32 + c);
-#pragma unroll
-  for (int d2 = 0; d2 < 4; ++d2) {
-    float o[NM];
-#pragma unroll
-    for (int m = 0; m < NM; ++m) o[m] = 0.f;
-#pragma unroll 4
-    for (int c = 0; c < 32; ++c) {
-      const float4* wr = reinterpret_cast<const float4*>(sw + (d2 * 32 + c) * 64);
-      float a = sb[c];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) {
-        const float4 w = wr[k];
-        a = fmaf(u[4 * k], w.x, a); a = fmaf(u[4 * k + 1], w.y, a); a = fmaf(u[4 * k + 2], w.z, a); a = fmaf(u[4 * k + 3], w.w, a);
-      }
-      a = gelu_erf_f(a);
-#pragma unroll
-      for (int m = 0; m < NM; ++m) o[m] = fmaf(hy[m][c], a, o[m]);
-    }
-    const int y = 2 * Y + (d2 >> 1), x = 2 * X + (d2 & 1);
-#pragma unroll
-    for (int m = 0; m < NM; ++m) low[((size_t(b) * NM + m) * 256 + y) * 256 + x] = o[m];
-  }
-}
 
 // gather rows: out[b][j][:] = in[b][t0 + j*tstride][:]   (mask tokens / iou token extraction, slicing)
 __global__ void gather_token_kernel(const float* __restrict__ in, int T, int t0, float* __restrict__ out, int B) {

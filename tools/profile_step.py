@@ -13,6 +13,7 @@ from samrs_b200.weights import synthetic_state_dict  # noqa: E402
 variant = sys.argv[1] if len(sys.argv) > 1 else "vit_h"
 eng = Engine(variant, "cuda:0")
 eng.load_state_dict(synthetic_state_dict(variant, 0))
+eng.set_graphs(False)                 # ncu lists plain launches; the graph replays the same kernels
 img = torch.from_numpy(synth.tile(0)).cuda()
 boxes = torch.from_numpy(synth.hboxes(0, 32)).cuda()
 labels = torch.from_numpy(synth.labels(0, 32)).to(torch.int32).cuda()
@@ -27,6 +28,7 @@ def step():
     eng.rle_encode(low_res=low, capacity=1 << 20)
 
 
+step()
 step()
 torch.cuda.synchronize()
 torch.cuda.cudart().cudaProfilerStart()
