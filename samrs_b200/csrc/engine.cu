@@ -496,13 +496,16 @@ static int sgemm(cudaStream_t st, const float* A, int lda, const float* W, int l
   if (K % 16 != 0 || lda % 4 != 0 || ldw % 4 != 0) SAMRS_FAIL("sgemm: K must be a multiple of 16");
   SgemmParams p{A, lda, W, ldw, C, ldc, bias, R, ldr, rmod, M, N, K, act};
   if (M <= 2048 && K % 64 == 0) {
-    // token-side GEMM: latency-bound, 64-deep k slices; split K >= 1024 across blockIdx.z (deterministic reduce)
-    int splits = 1;
+    // token-side GEMM: latency-bound; one shared-memory panel of at most 256 of K per block, larger K split across
+    // blockIdx.z (deterministic reduce)
     float* ws = t_ctx ? t_ctx->splitk_ws : nullptr;
-    if (K >= 1024 && ws && size_t(M) * N * 8 <= t_ctx->splitk_ws_floats) splits = 8;
-    const int kps = ((K / splits + 63) / 64) * 64;
-    dim3 grid((M + 63) / 64, (N + 63) / 64, splits);
-    sgemm_small_kernel<<<grid, 256, 0, st>>>(p, kps, splits > 1 ? ws : nullptr);
+    int splits = (K + SGT_KMAX - 1) / SGT_KMAX;
+    if (splits > 1 && !(ws && size_t(M) * N * splits <= t_ctx->splitk_ws_floats)) SAMRS_FAIL("sgemm: split-K workspace too small");
+    const int kps = ((K / splits + 15) / 16) * 16;
+    if (kps > SGT_KMAX || kps * splits < K) SAMRS_FAIL("sgemm: K does not split into panels of at most 256");
+    SAMRS_TRY(opt_in_smem(sgemm_small_kernel, SGT_SMEM));
+    dim3 grid((M + 31) / 32, (N + 31) / 32, splits);
+    sgemm_small_kernel<<<grid, 128, SGT_SMEM, st>>>(p, kps, splits > 1 ? ws : nullptr);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
     if (splits > 1) {

@@ -287,57 +287,74 @@ sgemm_tn_kernel(const SgemmParams p) {
   }
 }
 
-// Small-M variant for the token side of the decoder (M = prompts x tokens <= ~1k rows): these GEMMs are latency-
-// not throughput-bound, so the k-slice is 64 deep (4x fewer load->sync round trips) and K can be split across
-// blockIdx.z into a workspace that splitk_reduce_kernel folds deterministically (fixed summation order).
-__global__ void __launch_bounds__(256)
+// Small-M variant for the token side of the decoder (M = prompts x tokens <= ~2k rows): these GEMMs are latency- not
+// throughput-bound (a few MFLOP each, ~60 of them per decode), so the kernel is built around ONE round trip to memory:
+// a block of 128 threads owns a 32 x 32 output tile and at most 256 of K; it brings its whole A and W panels (32 rows x
+// 256 floats each, k contiguous, row pitch 260 floats = conflict-free float4 reads for rows 1 apart) into shared memory with
+// cp.async - every load of the block in flight at once - and then runs 64 float4 steps of 2 x 4 dot products per thread.
+// K > 256 is split across blockIdx.z into a workspace that splitk_reduce_kernel folds in a fixed order; the k order
+// inside a block is ascending, so results equal the previous kernel's (64-deep slices through transposed smem, 4 serial
+// load -> sync -> compute rounds and 8-way bank conflicts on the transposing stores: 17 us per launch against ~4 us).
+constexpr int SGT_KMAX = 256;
+constexpr int SGT_PITCH = SGT_KMAX + 4;
+constexpr int SGT_SMEM = 2 * 32 * SGT_PITCH * 4;
+__global__ void __launch_bounds__(128)
 sgemm_small_kernel(const SgemmParams p, int k_per_split, float* __restrict__ ws /*[splits][M][N] or null*/) {
-  __shared__ __align__(16) float As[64][64 + 4];
-  __shared__ __align__(16) float Ws[64][64 + 4];
+  extern __shared__ __align__(16) float sgt_smem[];
+  float* As = sgt_smem;
+  float* Ws = sgt_smem + 32 * SGT_PITCH;
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
-  const int kbeg = blockIdx.z * k_per_split, kend = min(p.K, kbeg + k_per_split);
-  const int ty = tid / 16, tx = tid % 16;
-  float acc[4][4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = kbeg; k0 < kend; k0 += 64) {
-    float4 ra[4], rw[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f = tid + 256 * i, r = f / 16, k4 = (f % 16) * 4;      // 64 rows x 16 float4
-      const int ar = m0 + r, wr = n0 + r;
-      ra[i] = (ar < p.M) ? *reinterpret_cast<const float4*>(p.A + size_t(ar) * p.lda + k0 + k4) : make_float4(0, 0, 0, 0);
-      rw[i] = (wr < p.N) ? *reinterpret_cast<const float4*>(p.W + size_t(wr) * p.ldw + k0 + k4) : make_float4(0, 0, 0, 0);
+  const int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  const int kbeg = blockIdx.z * k_per_split;
+  const int kn = min(p.K, kbeg + k_per_split) - kbeg;          // <= 256, multiple of 16 (host)
+  const int k4n = kn >> 2;
+  for (int i = tid; i < 32 * k4n; i += 128) {
+    const int r = i / k4n, c4 = i - r * k4n;
+    const int ar = m0 + r, wr = n0 + r;
+    float* da = As + r * SGT_PITCH + 4 * c4;
+    float* dw = Ws + r * SGT_PITCH + 4 * c4;
+    if (ar < p.M) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(da)), "l"(p.A + size_t(ar) * p.lda + kbeg + 4 * c4) : "memory");
+    } else {
+      *reinterpret_cast<float4*>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int f = tid + 256 * i, r = f / 16, k4 = (f % 16) * 4;
-      As[k4 + 0][r] = ra[i].x; As[k4 + 1][r] = ra[i].y; As[k4 + 2][r] = ra[i].z; As[k4 + 3][r] = ra[i].w;
-      Ws[k4 + 0][r] = rw[i].x; Ws[k4 + 1][r] = rw[i].y; Ws[k4 + 2][r] = rw[i].z; Ws[k4 + 3][r] = rw[i].w;
-    }
-    __syncthreads();
-#pragma unroll 16
-    for (int k = 0; k < 64; ++k) {
-      const float4 a = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 w = *reinterpret_cast<const float4*>(&Ws[k][tx * 4]);
-      const float av[4] = {a.x, a.y, a.z, a.w}, wv[4] = {w.x, w.y, w.z, w.w};
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], wv[j], acc[i][j]);
+    if (wr < p.N) {
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dw)), "l"(p.W + size_t(wr) * p.ldw + kbeg + 4 * c4) : "memory");
+    } else {
+      *reinterpret_cast<float4*>(dw) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  __syncthreads();
+  const int tm = tid >> 3, tn = tid & 7;                        // rows tm, tm + 16; columns tn, tn + 8, tn + 16, tn + 24
+  float acc[2][4];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+#pragma unroll 4
+  for (int c4 = 0; c4 < k4n; ++c4) {
+    float4 a[2], w[4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const float4*>(As + (tm + 16 * i) * SGT_PITCH + 4 * c4);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(Ws + (tn + 8 * j) * SGT_PITCH + 4 * c4);
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float v = acc[i][j];
+        v = fmaf(a[i].x, w[j].x, v); v = fmaf(a[i].y, w[j].y, v); v = fmaf(a[i].z, w[j].z, v); v = fmaf(a[i].w, w[j].w, v);
+        acc[i][j] = v;
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int m = m0 + tm + 16 * i;
     if (m >= p.M) continue;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+      const int n = n0 + tn + 8 * j;
       if (n >= p.N) continue;
       float v = acc[i][j];
       if (ws) { ws[(size_t(blockIdx.z) * p.M + m) * p.N + n] = v; continue; }
