@@ -396,7 +396,8 @@ struct Engine {
   __half *a_pe, *xn, *qkv, *attn_o, *hid, *x16, *neck_ln16, *neck_col;
   float *x, *rel, *neck0, *neck2, *feat_tok, *feat_nchw;
   // per-image decoder cache
-  float *src0, *K0, *V0, *Qi0;
+  float *src0, *KVQ0;                  // KVQ0 [4096][384] = layer-0 [K (t2i) | V (t2i) | Q (i2t)] of the image tokens
+  float *w_kvq0 = nullptr, *b_kvq0 = nullptr, *R_kvq0 = nullptr;   // their concatenated weights / biases / positional terms
   float* pp_full = nullptr;            // postprocess scratch for non-1024 sizes
   struct ResizeTab { int in, out, ksize; int* bounds; int* kk; std::vector<int> h_bounds, h_kk; unsigned long long used; };
   std::vector<ResizeTab> resize_tabs;   // Pillow tap tables per (input size, output size), built on first use; LRU of 32
@@ -817,6 +818,19 @@ static int load_weights_impl(Engine* e, const SrcMap& m, cudaStream_t st) {
     SAMRS_TRY(e->alloc(&e->pek[i], size_t(4096) * 128));
     SAMRS_TRY(sgemm(st, e->dense_pe, 256, pw[i], 256, e->pek[i], 128, nullptr, nullptr, 0, 0, 4096, 128, 256, 0));
   }
+  // layer-0 projections of the (prompt-independent) image tokens as one GEMM: [Wk ; Wv ; Wq], [bk ; bv ; bq], [pe Wk | 0 | pe Wq]
+  SAMRS_TRY(e->alloc(&e->w_kvq0, size_t(384) * 256));
+  SAMRS_TRY(e->alloc(&e->b_kvq0, 384));
+  SAMRS_TRY(e->alloc(&e->R_kvq0, size_t(4096) * 384));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->w_kvq0, e->dl[0].t2i.wk, size_t(128) * 256 * 4, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->w_kvq0 + size_t(128) * 256, e->dl[0].t2i.wv, size_t(128) * 256 * 4, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->w_kvq0 + size_t(256) * 256, e->dl[0].i2t.wq, size_t(128) * 256 * 4, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->b_kvq0, e->dl[0].t2i.bk, 512, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->b_kvq0 + 128, e->dl[0].t2i.bv, 512, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpyAsync(e->b_kvq0 + 256, e->dl[0].i2t.bq, 512, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemsetAsync(e->R_kvq0, 0, size_t(4096) * 384 * 4, st));
+  SAMRS_CUDA_OK(cudaMemcpy2DAsync(e->R_kvq0, 384 * 4, e->pek[0], 128 * 4, 128 * 4, 4096, cudaMemcpyDeviceToDevice, st));
+  SAMRS_CUDA_OK(cudaMemcpy2DAsync(e->R_kvq0 + 256, 384 * 4, e->pek[1], 128 * 4, 128 * 4, 4096, cudaMemcpyDeviceToDevice, st));
   // tensor-core decoder GEMMs (3-term split fp16): concatenated along N
   //   P1 = keys(l0) -> [K(l1 t2i) | V(l1 t2i) | Q(l1 i2t)]      N = 384
   //   P2 = keys(l1) -> [K(final)  | V(final)  | ConvT1 (4x64)]  N = 512
@@ -877,9 +891,7 @@ static int alloc_activations(Engine* e) {
   SAMRS_TRY(e->alloc(&e->feat_tok, T * 256));
   SAMRS_TRY(e->alloc(&e->feat_nchw, T * 256));
   SAMRS_TRY(e->alloc(&e->src0, T * 256));
-  SAMRS_TRY(e->alloc(&e->K0, T * 128));
-  SAMRS_TRY(e->alloc(&e->V0, T * 128));
-  SAMRS_TRY(e->alloc(&e->Qi0, T * 128));
+  SAMRS_TRY(e->alloc(&e->KVQ0, T * 384));
   e->ctx.splitk_ws_floats = size_t(8) * 1024 * 2048;
   SAMRS_TRY(e->alloc(&e->ctx.splitk_ws, e->ctx.splitk_ws_floats));
   return 0;
@@ -949,9 +961,8 @@ static int build_image_cache(Engine* e, cudaStream_t st) {
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   const DecLayer& L = e->dl[0];
-  SAMRS_TRY(sgemm(st, e->src0, 256, L.t2i.wk, 256, e->K0, 128, L.t2i.bk, e->pek[0], 128, 4096, 4096, 128, 256, 0));
-  SAMRS_TRY(sgemm(st, e->src0, 256, L.t2i.wv, 256, e->V0, 128, L.t2i.bv, nullptr, 0, 0, 4096, 128, 256, 0));
-  SAMRS_TRY(sgemm(st, e->src0, 256, L.i2t.wq, 256, e->Qi0, 128, L.i2t.bq, e->pek[1], 128, 4096, 4096, 128, 256, 0));
+  // one GEMM for the three layer-0 projections of the image tokens (192 blocks instead of three launches of 64)
+  SAMRS_TRY(sgemm(st, e->src0, 256, e->w_kvq0, 256, e->KVQ0, 384, e->b_kvq0, e->R_kvq0, 384, 4096, 4096, 384, 256, 0));
   e->image_set = true;
   return 0;
 }
@@ -1084,7 +1095,8 @@ constexpr int T2I_CHUNKS = 4;     // key chunks of the token -> image attention 
 static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, int multimask) {
   const int BT = B * T;
   // image-side layer-0 operands: shared across prompts unless a mask prompt makes src per-prompt
-  const float *K0 = e->K0, *V0 = e->V0, *Qi0 = e->Qi0, *src = e->src0;
+  const float *K0 = e->KVQ0, *V0 = e->KVQ0 + 128, *Qi0 = e->KVQ0 + 256, *src = e->src0;
+  int ld0 = 384;                       // row pitch of the layer-0 K / V / Q operands
   size_t kv_stride = 0;
   int src_mod = 4096;
   if (has_mask) {
@@ -1093,6 +1105,7 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
     SAMRS_TRY(sgemm(st, e->d_src, 256, L0.t2i.wv, 256, e->d_Vp, 128, L0.t2i.bv, nullptr, 0, 0, B * 4096, 128, 256, 0));
     SAMRS_TRY(sgemm(st, e->d_src, 256, L0.i2t.wq, 256, e->d_Qp, 128, L0.i2t.bq, e->pek[1], 128, 4096, B * 4096, 128, 256, 0));
     K0 = e->d_Kp; V0 = e->d_Vp; Qi0 = e->d_Qp; src = e->d_src;
+    ld0 = 128;
     kv_stride = size_t(4096) * 128;
     src_mod = 0;
   }
@@ -1116,7 +1129,7 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
     SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, L.t2i.wq, 256, e->d_tmp128a, 128, L.t2i.bq, nullptr, 0, 0, BT, 128, 256, 0));
     if (layer == 0) {
-      t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128a, K0, V0, 128, kv_stride, e->d_t2i_part, T);
+      t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128a, K0, V0, ld0, kv_stride, e->d_t2i_part, T);
     } else {
       // K | V | Q(i2t) projections of the per-prompt image tokens in one tensor-core GEMM
       SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p1, M4, 384, 768, e->d_P, 384, e->bias_p1, e->R1, 384, 4096));
@@ -1136,9 +1149,9 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
     SAMRS_TRY(sgemm(st, qpl, 256, L.i2t.wk, 256, e->d_tmp128a, 128, L.i2t.bk, nullptr, 0, 0, BT, 128, 256, 0));
     SAMRS_TRY(sgemm(st, queries, 256, L.i2t.wv, 256, e->d_tmp128b, 128, L.i2t.bv, nullptr, 0, 0, BT, 128, 256, 0));
     if (layer == 0)
-      i2t_attn_kernel<<<dim3(4096 / 128, B), 128, size_t(2) * T * 128 * 4, st>>>(Qi0, 128, kv_stride, e->d_tmp128a, e->d_tmp128b, e->d_ioA, T);
+      i2t_attn_kernel<<<dim3(4096 / I2T_TOK_PER_BLOCK, B), 256, size_t(2) * T * 8 * I2T_HP * 4, st>>>(Qi0, ld0, kv_stride, e->d_tmp128a, e->d_tmp128b, e->d_ioA, T);
     else
-      i2t_attn_kernel<<<dim3(4096 / 128, B), 128, size_t(2) * T * 128 * 4, st>>>(e->d_P + 256, 384, size_t(4096) * 384, e->d_tmp128a,
+      i2t_attn_kernel<<<dim3(4096 / I2T_TOK_PER_BLOCK, B), 256, size_t(2) * T * 8 * I2T_HP * 4, st>>>(e->d_P + 256, 384, size_t(4096) * 384, e->d_tmp128a,
                                                                                   e->d_tmp128b, e->d_ioA, T);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
