@@ -1,23 +1,14 @@
-// tcgen05 attention with decomposed relative-position bias for the SAM image encoder.
+// Parameters and tile geometry shared by the tcgen05 attention kernel (attn_tc2.cuh) of the SAM image encoder.
 //
-// One kernel template serves both block kinds of `Attention.forward`
-// (SA/modeling/image_encoder.py:224-240) + `add_decomposed_rel_pos` (:325-361):
-//   * 14x14 windowed blocks: one query tile = half a window (7 rows x 14 tokens = 98 queries),
-//     one key tile = the whole window (196 keys, zero-padded tokens included);
-//   * global blocks: query tile = 2 grid rows (128 queries), 32 key tiles of 2 grid rows (128 keys),
-//     streaming (online) softmax so the 4096x4096 score matrix is never materialised.
-// Tokens are addressed through one 3-D TMA tensor map over the qkv activation viewed as
-// [y=64][x=64][3*D] fp16; out-of-grid (padded) tokens are zero-filled by TMA.  Because the K bias only
-// shifts every score of a row by the same amount and the V bias adds bv to every output row
-// (softmax rows sum to 1), the qkv GEMM omits both and the V bias is folded into the proj bias;
-// zero-filled padded keys then reproduce the reference's "padded k,v = qkv bias" semantics exactly.
-//
-// Per CTA (persistent over (query tile, head) items), 256 threads:
-//   warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-7 softmax (1 query row / thread).
-//   S = Q K^T    : tcgen05.mma M128 x N(SN) x K16, Q and K tiles K-major SW128 in smem, fp32 S in TMEM
-//   softmax      : tcgen05.ld S -> scale + rel_h[kh] + rel_w[kw] (registers) -> exp2 -> fp16 P -> smem (SW128)
-//   O_j = P V_j  : A = P (K-major), B = V tile as loaded ([key][hd] = MN-major SW128), N = 64 (+16 for hd 80)
-//   O accumulates in registers with the usual running-max rescale; normalised and written as fp16.
+// `Attention.forward` (SA/modeling/image_encoder.py:224-240) + `add_decomposed_rel_pos` (:325-361) for both block kinds:
+//   * 14x14 windowed blocks: one query tile = half a window (7 rows x 14 tokens = 98 queries), one key tile = the whole
+//     window (196 keys, zero-padded tokens included);
+//   * global blocks: query tile = 2 grid rows (128 queries), 32 key tiles of 2 grid rows (128 keys), streaming (online)
+//     softmax so the 4096x4096 score matrix is never materialised.
+// Tokens are addressed through one 3-D TMA tensor map over the qkv activation viewed as [y=64][x=64][3*D] fp16;
+// out-of-grid (padded) tokens are zero-filled by TMA.  Because the K bias only shifts every score of a row by the same
+// amount and the V bias adds bv to every output row (softmax rows sum to 1), the qkv GEMM omits both and the V bias is
+// folded into the proj bias; zero-filled padded keys then reproduce the reference's "padded k,v = qkv bias" semantics.
 #pragma once
 #include "common.cuh"
 
@@ -26,16 +17,16 @@ namespace samrs {
 struct AttnParams {
   const float* rel;     // [heads][4096][NP] fp32 (NP = 256 global / 64 windowed), log2(e) * q.[rel_pos_h ; rel_pos_w]:
                         //   rel_h[kh] = rel[qh - kh + S-1],  rel_w[kw] = rel[(2S-1) + qw - kw + S-1]
-  const __half* rel16;  // attention v2: the same table already divided by scale_log2e and rounded to fp16
-                        //   (written by the rel-pos GEMM's epilogue; it is exactly the value the kernel used to compute)
+  const __half* rel16;  // global blocks: the same table already divided by scale_log2e and rounded to fp16 (written by the
+                        //   rel-pos GEMM's epilogue); windowed blocks compute their terms in the kernel and ignore it
   __half* out;          // [4096][D] fp16, head-major columns (h*HD + c)
   int D;                // embed dim
   int heads;
-  int num_qtiles;       // windowed: 25 windows * 2 halves; global: 32
+  int num_qtiles;       // query-tile PAIRS: windowed 25 (windows, two 7-row halves each); global 16
   float scale_log2e;    // hd^-0.5 * log2(e)
   float rel_scale;      // windowed blocks: 1 / scale_log2e, applied to G = q . log2e [rel_pos_h ; rel_pos_w]^T before it becomes R
   unsigned long long* dbg;   // optional pipeline trace of CTA 0 (tools/attn_trace.py)
-  int pv_split;         // attention v2, head dim 80: 1 = issue P.V as an N=64 and an N=16 MMA per k-step (first version), 0 = one N=80 MMA
+  int pv_split;         // head dim 80: 1 = issue P.V as an N=64 and an N=16 MMA per k-step (first version), 0 = one N=80 MMA
 };
 #ifdef SAMRS_EXPERIMENTS
 __device__ __forceinline__ void attn_dbg(const AttnParams& p, int slot) {

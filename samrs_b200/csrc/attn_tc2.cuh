@@ -386,7 +386,7 @@ attn_tc2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int qy = w ? qy1 : qy0;
       const int ty = qy + r / BX, tx = x0 + r % BX;
       const bool valid = (r < QR) && ty < 64 && tx < 64;
-      const int qh = qy - ky0 + r / BX, qw = r % BX;
+      const int qw = r % BX;
       if constexpr (NKT > 1) {
         // the rel-pos GEMM's epilogue wrote fp16(G / scale_log2e), i.e. the entries of the bias operand R themselves
         const __half* rrow = p.rel16 + (size_t(head) * 4096 + (valid ? ty * 64 + tx : 0)) * NP;

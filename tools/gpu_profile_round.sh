@@ -1,17 +1,18 @@
 #!/bin/bash
-# round evidence: tests, smoke, bench line, ncu launch list of one step, ncu --set full of the top kernels (1 GPU)
+# round evidence (1 GPU): ncu launch list of one step (cold-cache, serialised), ncu --set full of the top kernels.
+# gpurun brings back at most 64 MiB: the reports are reduced to their raw-metric CSV on the box; only the GEMM report is kept.
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -q -m gpu -x 2>&1 | tail -4 > gpurun_out/tests.log; cat gpurun_out/tests.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2
-timeout 900 python bench.py --steps 10 --warmup 3 > gpurun_out/bench.json 2> gpurun_out/bench.err
-tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json
-nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > gpurun_out/clocks_idle.csv
 timeout 600 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv \
   --log-file gpurun_out/launches.csv python tools/profile_step.py > gpurun_out/ncu1.log 2>&1
-timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_tc2_kernel -s 9 -c 4 \
-  -o gpurun_out/prof_gemm -f python tools/profile_step.py > gpurun_out/ncu2.log 2>&1
-timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:attn_tc2 -s 6 -c 2 \
-  -o gpurun_out/prof_attn -f python tools/profile_step.py > gpurun_out/ncu3.log 2>&1
-timeout 600 ncu --profile-from-start off --set full --clock-control none -k regex:"upsample4|ln_rows_stream|rle_" -c 6 \
-  -o gpurun_out/prof_epi -f python tools/profile_step.py > gpurun_out/ncu4.log 2>&1
-ls -la gpurun_out | head -30
+python tools/summarize_launches.py gpurun_out/launches.csv gpurun_out/launches_summary.csv | head -8
+cap() {  # name, kernel regex, skip, count
+  timeout 900 ncu --profile-from-start off --set full --clock-control none -k regex:"$2" -s $3 -c $4 \
+    -o gpurun_out/prof_$1 -f python tools/profile_step.py > gpurun_out/ncu_$1.log 2>&1
+  ncu -i gpurun_out/prof_$1.ncu-rep --page raw --csv > gpurun_out/prof_$1_raw.csv 2> /dev/null
+  [ "$1" = "gemm" ] || rm -f gpurun_out/prof_$1.ncu-rep
+}
+cap gemm "gemm_tc2_kernel" 9 4
+cap attn "attn_tc2" 6 2
+cap epi "upsample4|ln_rows_stream|rle_pack|rle_scan|coco_string" 0 8
+cap dec "t2i_attn|i2t_attn|sgemm_small|gemm_tc_kernel<128, false, 3|ln256_split|ln64_gelu" 0 8
+ls -la gpurun_out | head -30; du -sh gpurun_out

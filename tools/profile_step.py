@@ -25,7 +25,8 @@ def step():
     low, _ = eng.decode(boxes=boxes, multimask_output=False)
     eng.postprocess(low, (1024, 1024), (1024, 1024))
     eng.semantic_reduce(low, labels, canvas)
-    eng.rle_encode(low_res=low, capacity=1 << 20)
+    counts, offsets, _ = eng.rle_encode(low_res=low, capacity=1 << 23)
+    eng.rle_strings(counts, offsets)
 
 
 step()
