@@ -960,7 +960,6 @@ static int build_image_cache(Engine* e, cudaStream_t st) {
   add_rowvec_kernel<<<(4096 * 256 + 255) / 256, 256, 0, st>>>(e->feat_tok, 0, e->no_mask, e->src0, 4096, 256);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
-  const DecLayer& L = e->dl[0];
   // one GEMM for the three layer-0 projections of the image tokens (192 blocks instead of three launches of 64)
   SAMRS_TRY(sgemm(st, e->src0, 256, e->w_kvq0, 256, e->KVQ0, 384, e->b_kvq0, e->R_kvq0, 384, 4096, 4096, 384, 256, 0));
   e->image_set = true;
@@ -1318,7 +1317,7 @@ int samrs_postprocess(void* engine, const float* lowres, int NB, int in_h, int i
   if (in_h == 1024 && in_w == 1024 && out_h == 1024 && out_w == 1024) {
     for (int b0 = 0; b0 < NB; b0 += 32768) {
       const int nb = NB - b0 < 32768 ? NB - b0 : 32768;
-      upsample4_threshold_kernel<<<dim3(1, 1024, nb), 256, 0, st>>>(lowres + size_t(b0) * 65536, masks_out ? masks_out + size_t(b0) * 1048576 : nullptr,
+      upsample4_threshold_kernel<<<dim3(1, 257, nb), 256, 0, st>>>(lowres + size_t(b0) * 65536, masks_out ? masks_out + size_t(b0) * 1048576 : nullptr,
                                                                     logits_out ? logits_out + size_t(b0) * 1048576 : nullptr, nb);
     }
     count_launch();
@@ -1544,7 +1543,7 @@ int samrs_semantic_reduce(void* engine, const float* lowres, const int* class_id
   if (H != 1024 || W != 1024) return set_err(e, samrs::fail(__FILE__, __LINE__, "semantic_reduce: only 1024x1024 tiles are supported"));
   if (B < 1) return 0;
   ProfScope ps(PC_EPILOGUE, static_cast<cudaStream_t>(stream));
-  upsample4_paint_kernel<<<dim3(1, 1024), 256, 0, static_cast<cudaStream_t>(stream)>>>(lowres, class_ids, B, label_map);
+  upsample4_paint_kernel<<<dim3(4, 257), 64, 0, static_cast<cudaStream_t>(stream)>>>(lowres, class_ids, B, label_map);
   count_launch();
   if (cudaGetLastError() != cudaSuccess) return set_err(e, samrs::fail(__FILE__, __LINE__, "semantic_reduce launch failed"));
   return 0;
