@@ -145,6 +145,7 @@ def test_graph_replay_pdl_and_eager_launches_agree_bit_for_bit():
     """The encode body and the decode bodies are replayed as CUDA graphs from their third call on, and the GEMM /
     attention / LayerNorm kernels use programmatic dependent launch: both are scheduling changes only."""
     from samrs_b200 import synth
+    from samrs_b200.engine import Engine
     from samrs_b200.weights import synthetic_state_dict
     eng = Engine("vit_t80", "cuda:0")
     eng.load_state_dict(synthetic_state_dict("vit_t80", 0))
