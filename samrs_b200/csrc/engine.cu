@@ -299,6 +299,11 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
     if (bn != 128 || out_half || p.hyper == nullptr || p.low == nullptr) SAMRS_FAIL("gemm: the up-scaling epilogue needs a 128-wide fp32 tile and its operands");
     return launch_gemm_inst<128, false, 3>(tA, tB, tC, p, grid, stream);
   }
+  if (act == 4) {
+    if (bn != 256 || out_half || p.ln64_out == nullptr || p.ln64_col0 % 256 != 0 || (p.N - p.ln64_col0) % 64 != 0)
+      SAMRS_FAIL("gemm: the LayerNorm64 epilogue needs 256-wide fp32 tiles aligned to the normalised column range");
+    return launch_gemm_inst<256, false, 4>(tA, tB, tC, p, grid, stream);
+  }
 #define SAMRS_GEMM_CASE(BN_)                                                                        \
   if (bn == BN_) {                                                                                  \
     if (out_half && act == 0) return launch_gemm_inst<BN_, true, 0>(tA, tB, tC, p, grid, stream);       \
@@ -1014,11 +1019,14 @@ static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, flo
 // ------------------------------------------------------------------ decoder
 // C = A' W'^T / 256 + bias + R : 3-term split-fp16 product on the tcgen05 GEMM (near-fp32 accuracy)
 static int gemm_dec(Engine* e, cudaStream_t st, const __half* A3, const __half* W3, int M, int N, int K3, float* out, int ldc,
-                    const float* bias, const float* res, int ldr, int res_mod, int accumulate = 0) {
+                    const float* bias, const float* res, int ldr, int res_mod, int accumulate = 0, bool ln64_tail = false) {
   GemmParams p;
+  if (ln64_tail) {                                     // P2: columns [256, 512) = ConvT1 groups -> LN2d + GELU + split in the epilogue
+    p.ln64_gamma = e->up_lnw; p.ln64_beta = e->up_lnb; p.ln64_out = e->d_up1; p.ln64_col0 = 256;
+  }
   p.M = M; p.N = N; p.K = K3; p.out = out; p.ldc = ldc; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f; p.dbg = nullptr; p.dbg_mode = 0; p.accumulate = accumulate;
-  return launch_gemm_tc(A3, K3, W3, K3, p, false, 0, e->num_sms, st, 0);
+  return launch_gemm_tc(A3, K3, W3, K3, p, false, ln64_tail ? 4 : 0, e->num_sms, st, ln64_tail ? 256 : 0);
 }
 
 static int add2(cudaStream_t st, const float* a, const float* b, float* out, size_t n) {
@@ -1168,7 +1176,7 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
     const DecAttn& a = e->final_attn;
     SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, a.wq, 256, e->d_tmp128a, 128, a.bq, nullptr, 0, 0, BT, 128, 256, 0));
-    SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p2, M4, 512, 768, e->d_P, 512, e->bias_p2, e->R2, 512, 4096));
+    SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p2, M4, 512, 768, e->d_P, 512, e->bias_p2, e->R2, 512, 4096, 0, true));
     t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 512, size_t(4096) * 512, e->d_t2i_part, T);
     t2i_combine_kernel<<<(B * 8 * T * 16 + 255) / 256, 256, 0, st>>>(e->d_t2i_part, e->d_tmp128b, B, T, T2I_CHUNKS);
     SAMRS_CUDA_OK(cudaGetLastError());
@@ -1195,10 +1203,8 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
   // last layer restricted to the returned slice: rows m_first .. m_first+NM-1 of the (4,256) weight
   SAMRS_TRY(sgemm(st, e->d_hy_b, 256, e->iou_head.w[2] + m_first * 256, 256, e->d_iou_all, NM, e->iou_head.b[2] + m_first, nullptr, 0, 0, B, NM,
                   256, 0));
-  // upscaling: ConvT1 columns of P2 -> LN2d+GELU per 64-channel group (in place); ConvT2+GELU+hyper product follows outside
-  ln64_gelu_split_kernel<<<unsigned((size_t(M4) * 4 * 16 + 255) / 256), 256, 0, st>>>(e->d_P, 512, 256, e->up_lnw, e->up_lnb, M4, e->d_up1);
-  SAMRS_CUDA_OK(cudaGetLastError());
-  count_launch();
+  // upscaling: the ConvT1 columns of P2 were normalised, activated and split in that GEMM's epilogue (d_up1); ConvT2 + GELU +
+  // hyper-network product follow outside the graph (they write the caller's logits)
   return 0;
 }
 

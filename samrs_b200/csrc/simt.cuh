@@ -815,37 +815,6 @@ __global__ void ln256_split_kernel(const float* __restrict__ in, const float* __
 }
 
 
-// LayerNorm2d(64, eps 1e-6) + GELU of output_upscaling (SA/modeling/mask_decoder.py:54-57, common.py:31-43) on the 64-channel
-// groups base[row * ld + off + g * 64 + c], g < 4 (the ConvT1 columns of the fused projection GEMM); half a warp per group.
-// The result leaves as the 3-term split-fp16 A operand [hi | lo | hi] of the tensor-core ConvTranspose2 GEMM: row
-// (token * 4 + group) of out, 192 halves (precision recipe).
-__global__ void ln64_gelu_split_kernel(const float* __restrict__ base, int ld, int off, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, int rows, __half* __restrict__ out /*[rows*4][192]*/) {
-  const int gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;       // (row, group)
-  const int l16 = threadIdx.x & 15;
-  if (gidx >= rows * 4) return;
-  const float4 a = *(reinterpret_cast<const float4*>(base + size_t(gidx >> 2) * ld + off + (gidx & 3) * 64) + l16);
-  float s = (a.x + a.y) + (a.z + a.w);
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s * (1.0f / 64.0f);
-  const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
-  float q = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = 1.0f / sqrtf(q * (1.0f / 64.0f) + 1e-6f);
-  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + l16);
-  const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + l16);
-  const float y[4] = {gelu_erf_f(g.x * (d0 * rstd) + be.x), gelu_erf_f(g.y * (d1 * rstd) + be.y),
-                      gelu_erf_f(g.z * (d2 * rstd) + be.z), gelu_erf_f(g.w * (d3 * rstd) + be.w)};
-  __half hi[4], lo[4];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) split_f16(y[i], hi[i], lo[i]);
-  __half* o = out + size_t(gidx) * 192 + l16 * 4;
-  *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
-  *reinterpret_cast<uint2*>(o + 64) = *reinterpret_cast<const uint2*>(lo);
-  *reinterpret_cast<uint2*>(o + 128) = *reinterpret_cast<const uint2*>(hi);
-}
 // weight [N][K] fp32 -> split-fp16 [N][3K] = scale * [hi | hi | lo], matching activations stored [hi | lo | hi]
 __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, float scale, __half* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
