@@ -299,11 +299,6 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
     if (bn != 128 || out_half || p.hyper == nullptr || p.low == nullptr) SAMRS_FAIL("gemm: the up-scaling epilogue needs a 128-wide fp32 tile and its operands");
     return launch_gemm_inst<128, false, 3>(tA, tB, tC, p, grid, stream);
   }
-  if (act == 4) {
-    if (bn != 256 || out_half || p.ln64_out == nullptr || p.ln64_col0 % 256 != 0 || (p.N - p.ln64_col0) % 64 != 0)
-      SAMRS_FAIL("gemm: the LayerNorm64 epilogue needs 256-wide fp32 tiles aligned to the normalised column range");
-    return launch_gemm_inst<256, false, 4>(tA, tB, tC, p, grid, stream);
-  }
 #define SAMRS_GEMM_CASE(BN_)                                                                        \
   if (bn == BN_) {                                                                                  \
     if (out_half && act == 0) return launch_gemm_inst<BN_, true, 0>(tA, tB, tC, p, grid, stream);       \
@@ -402,7 +397,8 @@ struct Engine {
   float *x, *rel, *neck0, *neck2, *feat_tok, *feat_nchw;
   // per-image decoder cache
   float *src0, *KVQ0;                  // KVQ0 [4096][384] = layer-0 [K (t2i) | V (t2i) | Q (i2t)] of the image tokens
-  float *w_kvq0 = nullptr, *b_kvq0 = nullptr, *R_kvq0 = nullptr;   // their concatenated weights / biases / positional terms
+  float *b_kvq0 = nullptr, *R_kvq0 = nullptr;                      // their concatenated biases / positional terms
+  __half *wd_kvq0 = nullptr, *src0A = nullptr;                     // split-fp16 [Wk ; Wv ; Wq] (384 x 768) and src0 (4096 x 768)
   float* pp_full = nullptr;            // postprocess scratch for non-1024 sizes
   struct ResizeTab { int in, out, ksize; int* bounds; int* kk; std::vector<int> h_bounds, h_kk; unsigned long long used; };
   std::vector<ResizeTab> resize_tabs;   // Pillow tap tables per (input size, output size), built on first use; LRU of 32
@@ -824,12 +820,12 @@ static int load_weights_impl(Engine* e, const SrcMap& m, cudaStream_t st) {
     SAMRS_TRY(sgemm(st, e->dense_pe, 256, pw[i], 256, e->pek[i], 128, nullptr, nullptr, 0, 0, 4096, 128, 256, 0));
   }
   // layer-0 projections of the (prompt-independent) image tokens as one GEMM: [Wk ; Wv ; Wq], [bk ; bv ; bq], [pe Wk | 0 | pe Wq]
-  SAMRS_TRY(e->alloc(&e->w_kvq0, size_t(384) * 256));
+  SAMRS_TRY(e->alloc(&e->wd_kvq0, size_t(384) * 768));
   SAMRS_TRY(e->alloc(&e->b_kvq0, 384));
   SAMRS_TRY(e->alloc(&e->R_kvq0, size_t(4096) * 384));
-  SAMRS_CUDA_OK(cudaMemcpyAsync(e->w_kvq0, e->dl[0].t2i.wk, size_t(128) * 256 * 4, cudaMemcpyDeviceToDevice, st));
-  SAMRS_CUDA_OK(cudaMemcpyAsync(e->w_kvq0 + size_t(128) * 256, e->dl[0].t2i.wv, size_t(128) * 256 * 4, cudaMemcpyDeviceToDevice, st));
-  SAMRS_CUDA_OK(cudaMemcpyAsync(e->w_kvq0 + size_t(256) * 256, e->dl[0].i2t.wq, size_t(128) * 256 * 4, cudaMemcpyDeviceToDevice, st));
+  split_weight_kernel<<<(128 * 256 + 255) / 256, 256, 0, st>>>(e->dl[0].t2i.wk, 128, 256, 256.0f, e->wd_kvq0);
+  split_weight_kernel<<<(128 * 256 + 255) / 256, 256, 0, st>>>(e->dl[0].t2i.wv, 128, 256, 256.0f, e->wd_kvq0 + size_t(128) * 768);
+  split_weight_kernel<<<(128 * 256 + 255) / 256, 256, 0, st>>>(e->dl[0].i2t.wq, 128, 256, 256.0f, e->wd_kvq0 + size_t(256) * 768);
   SAMRS_CUDA_OK(cudaMemcpyAsync(e->b_kvq0, e->dl[0].t2i.bk, 512, cudaMemcpyDeviceToDevice, st));
   SAMRS_CUDA_OK(cudaMemcpyAsync(e->b_kvq0 + 128, e->dl[0].t2i.bv, 512, cudaMemcpyDeviceToDevice, st));
   SAMRS_CUDA_OK(cudaMemcpyAsync(e->b_kvq0 + 256, e->dl[0].i2t.bq, 512, cudaMemcpyDeviceToDevice, st));
@@ -897,6 +893,7 @@ static int alloc_activations(Engine* e) {
   SAMRS_TRY(e->alloc(&e->feat_nchw, T * 256));
   SAMRS_TRY(e->alloc(&e->src0, T * 256));
   SAMRS_TRY(e->alloc(&e->KVQ0, T * 384));
+  SAMRS_TRY(e->alloc(&e->src0A, T * 768));
   e->ctx.splitk_ws_floats = size_t(8) * 1024 * 2048;
   SAMRS_TRY(e->alloc(&e->ctx.splitk_ws, e->ctx.splitk_ws_floats));
   return 0;
@@ -961,12 +958,15 @@ static int gemm_enc(Engine* e, cudaStream_t st, const __half* A, int lda, const 
 }
 
 // per-image decoder cache: src0 = features + no_mask_embed and its three layer-0 projections
+static int gemm_dec(Engine* e, cudaStream_t st, const __half* A3, const __half* W3, int M, int N, int K3, float* out, int ldc,
+                    const float* bias, const float* res, int ldr, int res_mod, int accumulate);
+
 static int build_image_cache(Engine* e, cudaStream_t st) {
-  add_rowvec_kernel<<<(4096 * 256 + 255) / 256, 256, 0, st>>>(e->feat_tok, 0, e->no_mask, e->src0, 4096, 256);
+  add_rowvec_split_kernel<<<(4096 * 64 + 255) / 256, 256, 0, st>>>(e->feat_tok, e->no_mask, e->src0, e->src0A, 4096, 256);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
-  // one GEMM for the three layer-0 projections of the image tokens (192 blocks instead of three launches of 64)
-  SAMRS_TRY(sgemm(st, e->src0, 256, e->w_kvq0, 256, e->KVQ0, 384, e->b_kvq0, e->R_kvq0, 384, 4096, 4096, 384, 256, 0));
+  // one tensor-core GEMM (3-term split fp16) for the three layer-0 projections of the image tokens: [K | V | Q] = src0 [Wk ; Wv ; Wq]^T
+  SAMRS_TRY(gemm_dec(e, st, e->src0A, e->wd_kvq0, 4096, 384, 768, e->KVQ0, 384, e->b_kvq0, e->R_kvq0, 384, 4096, 0));
   e->image_set = true;
   return 0;
 }
@@ -1019,14 +1019,13 @@ static int encode_impl(Engine* e, const uint8_t* img, int H, int W, int chw, flo
 // ------------------------------------------------------------------ decoder
 // C = A' W'^T / 256 + bias + R : 3-term split-fp16 product on the tcgen05 GEMM (near-fp32 accuracy)
 static int gemm_dec(Engine* e, cudaStream_t st, const __half* A3, const __half* W3, int M, int N, int K3, float* out, int ldc,
-                    const float* bias, const float* res, int ldr, int res_mod, int accumulate = 0, bool ln64_tail = false) {
+                    const float* bias, const float* res, int ldr, int res_mod, int accumulate = 0);
+static int gemm_dec(Engine* e, cudaStream_t st, const __half* A3, const __half* W3, int M, int N, int K3, float* out, int ldc,
+                    const float* bias, const float* res, int ldr, int res_mod, int accumulate) {
   GemmParams p;
-  if (ln64_tail) {                                     // P2: columns [256, 512) = ConvT1 groups -> LN2d + GELU + split in the epilogue
-    p.ln64_gamma = e->up_lnw; p.ln64_beta = e->up_lnb; p.ln64_out = e->d_up1; p.ln64_col0 = 256;
-  }
   p.M = M; p.N = N; p.K = K3; p.out = out; p.ldc = ldc; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f; p.dbg = nullptr; p.dbg_mode = 0; p.accumulate = accumulate;
-  return launch_gemm_tc(A3, K3, W3, K3, p, false, ln64_tail ? 4 : 0, e->num_sms, st, ln64_tail ? 256 : 0);
+  return launch_gemm_tc(A3, K3, W3, K3, p, false, 0, e->num_sms, st, 0);
 }
 
 static int add2(cudaStream_t st, const float* a, const float* b, float* out, size_t n) {
@@ -1176,7 +1175,7 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
     const DecAttn& a = e->final_attn;
     SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, a.wq, 256, e->d_tmp128a, 128, a.bq, nullptr, 0, 0, BT, 128, 256, 0));
-    SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p2, M4, 512, 768, e->d_P, 512, e->bias_p2, e->R2, 512, 4096, 0, true));
+    SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p2, M4, 512, 768, e->d_P, 512, e->bias_p2, e->R2, 512, 4096));
     t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 512, size_t(4096) * 512, e->d_t2i_part, T);
     t2i_combine_kernel<<<(B * 8 * T * 16 + 255) / 256, 256, 0, st>>>(e->d_t2i_part, e->d_tmp128b, B, T, T2I_CHUNKS);
     SAMRS_CUDA_OK(cudaGetLastError());
@@ -1203,8 +1202,10 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
   // last layer restricted to the returned slice: rows m_first .. m_first+NM-1 of the (4,256) weight
   SAMRS_TRY(sgemm(st, e->d_hy_b, 256, e->iou_head.w[2] + m_first * 256, 256, e->d_iou_all, NM, e->iou_head.b[2] + m_first, nullptr, 0, 0, B, NM,
                   256, 0));
-  // upscaling: the ConvT1 columns of P2 were normalised, activated and split in that GEMM's epilogue (d_up1); ConvT2 + GELU +
-  // hyper-network product follow outside the graph (they write the caller's logits)
+  // upscaling: ConvT1 columns of P2 -> LN2d+GELU per 64-channel group (in place); ConvT2+GELU+hyper product follows outside
+  ln64_gelu_split_kernel<<<unsigned((size_t(M4) * 4 * 16 + 255) / 256), 256, 0, st>>>(e->d_P, 512, 256, e->up_lnw, e->up_lnb, M4, e->d_up1);
+  SAMRS_CUDA_OK(cudaGetLastError());
+  count_launch();
   return 0;
 }
 

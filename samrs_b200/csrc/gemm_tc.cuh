@@ -33,12 +33,6 @@ struct GemmParams {
   int accumulate;       // fp32 output only: out += result (TMA reduce-add) instead of out = result
   int dbg_mode;         // tools only (results are garbage): bit0 skip TMA loads, bit1 skip MMAs, bit2 skip the epilogue
   // ACT == 3 (mask decoder, second up-scaling stage fused with the hyper-network product; see gemm_epilogue_warp_upscale2):
-  // ACT == 4: column tiles with n0 >= ln64_col0 hold 64-channel groups that get LayerNorm2d + GELU in the epilogue and leave
-  // as the split-fp16 operand of the next GEMM (gemm_epilogue_warp_ln64); tiles below ln64_col0 take the plain fp32 epilogue
-  const float* ln64_gamma = nullptr;
-  const float* ln64_beta = nullptr;
-  __half* ln64_out = nullptr;     // [M * groups][192] = [hi(64) | lo(64) | hi(64)]
-  int ln64_col0 = 0;
   const float* hyper = nullptr;   // [B][hyper_nm][32]
   float* low = nullptr;           // [B][hyper_nm][256][256] low-res mask logits
   int hyper_nm = 0;
@@ -84,7 +78,6 @@ struct GemmCfg {
 // erfc(z) ~= 2^(-z Q(z)) on [0, 4] (Q = degree-5 least-squares fit of -log2(erfc z) / z, tools/fit_gelu.py): |error| < 3e-7,
 // far below the fp16 rounding of the result.  One MUFU op and ten FP32 ops per element: the epilogue of lin1 is bound
 // by MUFU / issue slots, erff costs ~30 instructions and the Abramowitz-Stegun 7.1.26 form used before two MUFU ops.
-__device__ __forceinline__ float gelu_erf_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
   float q = fmaf(z, -2.635702863e-04f, 4.330650429e-03f);
@@ -188,67 +181,6 @@ __device__ __forceinline__ void gemm_epilogue_warp_upscale2(const GemmParams& p,
   }
 }
 
-// ACT == 4, tiles at n0 >= ln64_col0: the first up-scaling stage of the mask decoder finished in registers.  The tile's
-// columns are the four (dy, dx) groups x 64 channels of ConvTranspose2d(256 -> 64, k2 s2) (mask_decoder.py:54); every
-// thread owns one image token's row, so LayerNorm2d over a group's 64 channels (common.py:31-43, eps 1e-6) and the GELU
-// (:57) need no communication.  The result is written straight as the 3-term split-fp16 A operand of the ConvT2 GEMM,
-// row (token * 4 + group): [hi(64) | lo(64) | hi(64)] - the fp32 (B,64,128,128) tensor never reaches memory.
-template <int BN>
-__device__ __forceinline__ void gemm_epilogue_warp_ln64(const GemmParams& p, uint32_t t_addr, int row0, int n0, float oscale, int lane,
-                                                        const float (&bias_r)[(BN + 31) / 32], int chunk_begin, int chunk_end) {
-  const int m = row0 + lane;
-  const bool ok = m < p.M;
-  const int groups = (p.N - p.ln64_col0) / 64;
-#pragma unroll
-  for (int c = 0; c < BN / 32; c += 2) {
-    if (c < chunk_begin || c >= chunk_end) continue;
-    if (n0 + c * 32 >= p.N) break;
-    uint32_t v0[32], v1[32];
-    tmem_ld32(t_addr + uint32_t(c * 32), v0);
-    tmem_ld32(t_addr + uint32_t((c + 1) * 32), v1);
-    tc_wait_ld();
-    float f[64];
-    float s = 0.f;
-#pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      f[j] = fmaf(__uint_as_float(v0[j]), oscale, __shfl_sync(0xffffffffu, bias_r[c], j));
-      f[32 + j] = fmaf(__uint_as_float(v1[j]), oscale, __shfl_sync(0xffffffffu, bias_r[c + 1], j));
-    }
-#pragma unroll
-    for (int j = 0; j < 64; ++j) s += f[j];
-    const float mean = s * (1.0f / 64.0f);
-    float q = 0.f;
-#pragma unroll
-    for (int j = 0; j < 64; ++j) { f[j] -= mean; q = fmaf(f[j], f[j], q); }
-    const float rstd = 1.0f / sqrtf(q * (1.0f / 64.0f) + 1e-6f);
-    const int g = (n0 - p.ln64_col0) / 64 + c / 2;
-    __half* orow = p.ln64_out + (size_t(ok ? m : 0) * groups + g) * 192;
-#pragma unroll
-    for (int j8 = 0; j8 < 8; ++j8) {                       // 8 channels per step: one uint4 of hi and one of lo
-      __half hi[8], lo[8];
-#pragma unroll
-      for (int h4 = 0; h4 < 2; ++h4) {
-        const float4 ga = __ldg(reinterpret_cast<const float4*>(p.ln64_gamma) + 2 * j8 + h4);
-        const float4 be = __ldg(reinterpret_cast<const float4*>(p.ln64_beta) + 2 * j8 + h4);
-        const int j = 8 * j8 + 4 * h4;
-        const float y0 = gelu_erf_exact(ga.x * (f[j] * rstd) + be.x), y1 = gelu_erf_exact(ga.y * (f[j + 1] * rstd) + be.y);
-        const float y2 = gelu_erf_exact(ga.z * (f[j + 2] * rstd) + be.z), y3 = gelu_erf_exact(ga.w * (f[j + 3] * rstd) + be.w);
-        const float y[4] = {y0, y1, y2, y3};
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          hi[4 * h4 + t] = __float2half_rn(y[t]);
-          lo[4 * h4 + t] = __float2half_rn(y[t] - __half2float(hi[4 * h4 + t]));
-        }
-      }
-      if (ok) {
-        reinterpret_cast<uint4*>(orow)[j8] = *reinterpret_cast<const uint4*>(hi);
-        reinterpret_cast<uint4*>(orow + 64)[j8] = *reinterpret_cast<const uint4*>(lo);
-        reinterpret_cast<uint4*>(orow + 128)[j8] = *reinterpret_cast<const uint4*>(hi);
-      }
-    }
-  }
-}
-
 // Epilogue of one accumulator tile, executed by one warp for its 32 TMEM lanes (rows row0 .. row0+31), 32 columns at
 // a time: tcgen05.ld -> scale + bias (+ residual) + activation in registers -> the warp's 32x32 block is staged in
 // shared memory and written out by ONE asynchronous TMA store (rows / columns beyond M / N are clipped by the TMA
@@ -268,12 +200,6 @@ __device__ __forceinline__ void gemm_epilogue_warp(const GemmParams& p, const CU
   if constexpr (ACT == 3) {
     gemm_epilogue_warp_upscale2<BN>(p, t_addr, row0, oscale, lane, bias_r, chunk_begin, chunk_end);
     return;
-  }
-  if constexpr (ACT == 4) {
-    if (n0 >= p.ln64_col0) {
-      gemm_epilogue_warp_ln64<BN>(p, t_addr, row0, n0, oscale, lane, bias_r, chunk_begin, chunk_end);
-      return;
-    }
   }
   constexpr int NCH = (BN + 31) / 32;
   const int row = row0 + lane;

@@ -379,14 +379,6 @@ __global__ void splitk_reduce_kernel(const SgemmParams p, const float* __restric
   p.C[size_t(m) * p.ldc + n] = v;
 }
 
-// out[r][c] = a[r % amod][c] + b[c] (+ r-indexed table)   -- small broadcast adds used by the decoder set-up
-__global__ void add_rowvec_kernel(const float* __restrict__ a, int amod, const float* __restrict__ vec, float* __restrict__ out,
-                                  int rows, int C) {
-  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= size_t(rows) * C) return;
-  const int r = int(i / C), c = int(i % C);
-  out[i] = a[size_t(amod > 0 ? r % amod : r) * C + c] + (vec ? vec[c] : 0.f);
-}
 __global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, size_t n) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i < n) a[i] += b[i];
@@ -701,6 +693,26 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
   lo = __float2half_rn(v - __half2float(hi));
 }
 
+// src0 = image embedding + no_mask_embed (mask_decoder.py:136 with the dense "no mask" prompt, prompt_encoder.py:165-168), written
+// as fp32 (residual of the first image-side update) and as the split-fp16 A operand [hi | lo | hi] of the layer-0 projection GEMM
+__global__ void add_rowvec_split_kernel(const float* __restrict__ a, const float* __restrict__ vec, float* __restrict__ out,
+                                        __half* __restrict__ out_split /*[rows][3 * C]*/, int rows, int C) {
+  const size_t i4 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;          // 4 consecutive channels
+  if (i4 * 4 >= size_t(rows) * C) return;
+  const int r = int(i4 * 4 / C), c = int(i4 * 4 % C);
+  const float4 x = *reinterpret_cast<const float4*>(a + i4 * 4);
+  const float4 v = *reinterpret_cast<const float4*>(vec + c);
+  const float y[4] = {x.x + v.x, x.y + v.y, x.z + v.z, x.w + v.w};
+  *reinterpret_cast<float4*>(out + i4 * 4) = make_float4(y[0], y[1], y[2], y[3]);
+  __half hi[4], lo[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) split_f16(y[t], hi[t], lo[t]);
+  __half* o = out_split + size_t(r) * 3 * C + c;
+  *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(o + C) = *reinterpret_cast<const uint2*>(lo);
+  *reinterpret_cast<uint2*>(o + 2 * C) = *reinterpret_cast<const uint2*>(hi);
+}
+
 // (3) image -> token cross attention: Q rows of `ldq` floats, prompt stride q_bstride (0 = shared); k,v [B][T][128].
 //     One thread per (image token, head): the 8 threads of a token read its 512-byte Q row and write the three 256-byte
 //     segments of its output row together, so every warp-wide access is four whole rows.  The prompt's k,v sit in shared
@@ -815,6 +827,37 @@ __global__ void ln256_split_kernel(const float* __restrict__ in, const float* __
 }
 
 
+// LayerNorm2d(64, eps 1e-6) + GELU of output_upscaling (SA/modeling/mask_decoder.py:54-57, common.py:31-43) on the 64-channel
+// groups base[row * ld + off + g * 64 + c], g < 4 (the ConvT1 columns of the fused projection GEMM); half a warp per group.
+// The result leaves as the 3-term split-fp16 A operand [hi | lo | hi] of the tensor-core ConvTranspose2 GEMM: row
+// (token * 4 + group) of out, 192 halves (precision recipe).
+__global__ void ln64_gelu_split_kernel(const float* __restrict__ base, int ld, int off, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, int rows, __half* __restrict__ out /*[rows*4][192]*/) {
+  const int gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;       // (row, group)
+  const int l16 = threadIdx.x & 15;
+  if (gidx >= rows * 4) return;
+  const float4 a = *(reinterpret_cast<const float4*>(base + size_t(gidx >> 2) * ld + off + (gidx & 3) * 64) + l16);
+  float s = (a.x + a.y) + (a.z + a.w);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * (1.0f / 64.0f);
+  const float d0 = a.x - mean, d1 = a.y - mean, d2 = a.z - mean, d3 = a.w - mean;
+  float q = (d0 * d0 + d1 * d1) + (d2 * d2 + d3 * d3);
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q * (1.0f / 64.0f) + 1e-6f);
+  const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + l16);
+  const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + l16);
+  const float y[4] = {gelu_erf_f(g.x * (d0 * rstd) + be.x), gelu_erf_f(g.y * (d1 * rstd) + be.y),
+                      gelu_erf_f(g.z * (d2 * rstd) + be.z), gelu_erf_f(g.w * (d3 * rstd) + be.w)};
+  __half hi[4], lo[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) split_f16(y[i], hi[i], lo[i]);
+  __half* o = out + size_t(gidx) * 192 + l16 * 4;
+  *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(o + 64) = *reinterpret_cast<const uint2*>(lo);
+  *reinterpret_cast<uint2*>(o + 128) = *reinterpret_cast<const uint2*>(hi);
+}
 // weight [N][K] fp32 -> split-fp16 [N][3K] = scale * [hi | hi | lo], matching activations stored [hi | lo | hi]
 __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, float scale, __half* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
