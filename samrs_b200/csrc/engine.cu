@@ -417,7 +417,7 @@ struct Engine {
   int dec_cap = 0;
   float *d_tok0 = nullptr, *d_q = nullptr, *d_tmp256a = nullptr, *d_tmp256b = nullptr, *d_tmp256c = nullptr, *d_tmp256d = nullptr;
   float *d_tmp128a = nullptr, *d_tmp128b = nullptr, *d_tmp128c = nullptr, *d_mlp = nullptr;
-  float *d_keys = nullptr, *d_P = nullptr, *d_hyper = nullptr, *d_hy_t = nullptr, *d_hy_a = nullptr, *d_hy_b = nullptr, *d_iou_all = nullptr, *d_low = nullptr;
+  float *d_keys = nullptr, *d_P = nullptr, *d_hyper = nullptr, *d_hy_a = nullptr, *d_hy_b = nullptr, *d_iou_all = nullptr, *d_low = nullptr;
   __half *d_keysA = nullptr, *d_ioA = nullptr, *d_up1 = nullptr;   // d_up1: split-fp16 GELU(LN(ConvT1)) [cap*16384][192]
   int mask_cap = 0;                    // mask-prompt path scratch (per-prompt layer-0 operands), allocated on first use
   float *d_Kp = nullptr, *d_Vp = nullptr, *d_Qp = nullptr, *d_src = nullptr;
@@ -922,7 +922,6 @@ static int ensure_decoder_scratch(Engine* e, int B) {
   e->release(&e->d_ioA); SAMRS_TRY(e->alloc(&e->d_ioA, c * 4096 * 384));
   e->release(&e->d_up1); SAMRS_TRY(e->alloc(&e->d_up1, c * 16384 * 192));
   e->release(&e->d_hyper); SAMRS_TRY(e->alloc(&e->d_hyper, c * 4 * 32));
-  e->release(&e->d_hy_t); SAMRS_TRY(e->alloc(&e->d_hy_t, c * 256));
   e->release(&e->d_hy_a); SAMRS_TRY(e->alloc(&e->d_hy_a, c * 256));
   e->release(&e->d_hy_b); SAMRS_TRY(e->alloc(&e->d_hy_b, c * 256));
   e->release(&e->d_iou_all); SAMRS_TRY(e->alloc(&e->d_iou_all, c * 4));
@@ -1029,9 +1028,8 @@ static int gemm_dec(Engine* e, cudaStream_t st, const __half* A3, const __half* 
 }
 
 static int add2(cudaStream_t st, const float* a, const float* b, float* out, size_t n) {
-  // out = a + b (elementwise, same shape) via the row-vector kernel with C = n
-  if (out != a) SAMRS_CUDA_OK(cudaMemcpyAsync(out, a, n * 4, cudaMemcpyDeviceToDevice, st));
-  add_inplace_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(out, b, n);
+  // out = a + b (elementwise, same shape; out may be a)
+  add_out_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(a, b, out, n);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
@@ -1187,17 +1185,12 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
   const int NM = multimask ? 3 : 1, m_first = multimask ? 1 : 0;
   for (int j = 0; j < NM; ++j) {
     const Mlp3& h = e->hyper[m_first + j];
-    gather_token_kernel<<<(B * 256 + 255) / 256, 256, 0, st>>>(queries, T, 1 + m_first + j, e->d_hy_t, B);
-    SAMRS_CUDA_OK(cudaGetLastError());
-    count_launch();
-    SAMRS_TRY(sgemm(st, e->d_hy_t, 256, h.w[0], 256, e->d_hy_a, 256, h.b[0], nullptr, 0, 0, B, 256, 256, 1));
+    // the mask token of every prompt is read in place: row stride T * 256 selects token 1 + m_first + j
+    SAMRS_TRY(sgemm(st, queries + size_t(1 + m_first + j) * 256, T * 256, h.w[0], 256, e->d_hy_a, 256, h.b[0], nullptr, 0, 0, B, 256, 256, 1));
     SAMRS_TRY(sgemm(st, e->d_hy_a, 256, h.w[1], 256, e->d_hy_b, 256, h.b[1], nullptr, 0, 0, B, 256, 256, 1));
     SAMRS_TRY(sgemm(st, e->d_hy_b, 256, h.w[2], 256, e->d_hyper + j * 32, NM * 32, h.b[2], nullptr, 0, 0, B, 32, 256, 0));
   }
-  gather_token_kernel<<<(B * 256 + 255) / 256, 256, 0, st>>>(queries, T, 0, e->d_hy_t, B);
-  SAMRS_CUDA_OK(cudaGetLastError());
-  count_launch();
-  SAMRS_TRY(sgemm(st, e->d_hy_t, 256, e->iou_head.w[0], 256, e->d_hy_a, 256, e->iou_head.b[0], nullptr, 0, 0, B, 256, 256, 1));
+  SAMRS_TRY(sgemm(st, queries, T * 256, e->iou_head.w[0], 256, e->d_hy_a, 256, e->iou_head.b[0], nullptr, 0, 0, B, 256, 256, 1));   // iou token = row 0
   SAMRS_TRY(sgemm(st, e->d_hy_a, 256, e->iou_head.w[1], 256, e->d_hy_b, 256, e->iou_head.b[1], nullptr, 0, 0, B, 256, 256, 1));
   // last layer restricted to the returned slice: rows m_first .. m_first+NM-1 of the (4,256) weight
   SAMRS_TRY(sgemm(st, e->d_hy_b, 256, e->iou_head.w[2] + m_first * 256, 256, e->d_iou_all, NM, e->iou_head.b[2] + m_first, nullptr, 0, 0, B, NM,

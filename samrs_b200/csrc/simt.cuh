@@ -379,9 +379,10 @@ __global__ void splitk_reduce_kernel(const SgemmParams p, const float* __restric
   p.C[size_t(m) * p.ldc + n] = v;
 }
 
-__global__ void add_inplace_kernel(float* __restrict__ a, const float* __restrict__ b, size_t n) {
+// out = a + b (queries + query_pe of the two-way blocks, transformer.py:164,176; out may alias a)
+__global__ void add_out_kernel(const float* a, const float* __restrict__ b, float* out, size_t n) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) a[i] += b[i];
+  if (i < n) out[i] = a[i] + b[i];
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -872,12 +873,6 @@ __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, f
 }
 
 
-// gather rows: out[b][j][:] = in[b][t0 + j*tstride][:]   (mask tokens / iou token extraction, slicing)
-__global__ void gather_token_kernel(const float* __restrict__ in, int T, int t0, float* __restrict__ out, int B) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= B * 256) return;
-  out[i] = in[(size_t(i / 256) * T + t0) * 256 + i % 256];
-}
 
 // ------------------------------------------------------------------------------------------------
 // Fused post-processing (SA/modeling/sam.py:133-162 + SA/predictor.py:242-243 + the driver's painter,
