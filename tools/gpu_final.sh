@@ -5,3 +5,5 @@ timeout 900 python -m pytest tests -q -m gpu 2>&1 | tail -3
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
 timeout 900 python bench.py > gpurun_out/bench_final.json 2> gpurun_out/bench_final.err
 tail -2 gpurun_out/bench_final.err; cat gpurun_out/bench_final.json
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_final_ref.json 2> gpurun_out/bench_final_ref.err
+cat gpurun_out/bench_final_ref.json | cut -c1-400
