@@ -60,6 +60,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- gpu-scope flags (stream-K ordering of partial sums)
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_gpu_add(int* p, int v) {
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // ---------------------------------------------------------------- programmatic dependent launch
 // A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may become resident while its predecessor in
 // the stream is still running: pdl_trigger() (executed by every CTA of the predecessor, here at its very start) lets the
@@ -143,6 +153,15 @@ __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m
   asm volatile(
       "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
+      : "memory");
+}
+// The same load multicast to the CTAs of `mask`: the box lands at this CTA-relative offset in each of them and the bytes are
+// credited, per destination, to the barrier at this CTA-relative offset in the LEADER (even rank) of that destination's pair
+// (peer bit 24 of the barrier address clear).
+__device__ __forceinline__ void tma_load_2d_pair_mcast(void* dst, const CUtensorMap* m, const uint64_t* bar_local, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar_local) & 0xFEFFFFFFu), "r"(c0), "r"(c1), "h"(mask)
       : "memory");
 }
 template <int COLS>

@@ -116,6 +116,7 @@ struct LaunchCtx {
   Profiler prof;
   float* splitk_ws = nullptr;                     // split-K partial sums of the token-side SGEMMs
   size_t splitk_ws_floats = 0;
+  int* sk_flags = nullptr;                        // stream-K tile counters of the encoder GEMMs (zero between launches)
   std::unordered_set<const void*> smem_opted;     // kernels whose dynamic-smem limit was raised on this engine's device
   bool capturing = false;                         // a CUDA graph is being captured: no events, no attribute calls
   bool pdl = true;                                // programmatic dependent launch for the kernels that support it
@@ -177,14 +178,62 @@ static int launch_gemm_mc_inst(const CUtensorMap& tA, const CUtensorMap& tB, con
 }
 #endif
 
-template <int BN, bool OH, int ACT>
+template <int BN, bool OH, int ACT, int EW = GEMM_EPI_WARPS>
 static int launch_gemm2_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const CUtensorMap& tC16, const GemmParams& p, int grid, cudaStream_t st) {
-  using Cfg = Gemm2Cfg<BN>;
-  SAMRS_TRY(opt_in_smem(gemm_tc2_kernel<BN, OH, ACT>, Cfg::kSmemBytes));
-  SAMRS_CUDA_OK(launch_pdl(gemm_tc2_kernel<BN, OH, ACT>, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, tA, tB, tC, tC16, p));
+  using Cfg = Gemm2Cfg<BN, EW>;
+  SAMRS_TRY(opt_in_smem(gemm_tc2_kernel<BN, OH, ACT, EW>, Cfg::kSmemBytes));
+  SAMRS_CUDA_OK(launch_pdl(gemm_tc2_kernel<BN, OH, ACT, EW>, dim3(grid), dim3(Cfg::kThreads), Cfg::kSmemBytes, st, tA, tB, tC, tC16, p));
   count_launch();
   return 0;
 }
+
+#ifdef SAMRS_EXPERIMENTS
+// clusters of four: how many fit on the device at once depends on how the SMs are spread over GPCs, so the grid is sized from
+// the occupancy query (once per kernel and engine device)
+template <int BN, bool OH, int ACT>
+static int launch_gemm4_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int supers, int num_sms, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN>;
+  SAMRS_TRY(opt_in_smem(gemm_tc4_kernel<BN, OH, ACT>, Cfg::kSmemBytes));
+  static int max_clusters = -1;
+  if (max_clusters < 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(num_sms & ~3); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension; at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_tc4_kernel<BN, OH, ACT>, &cfg) != cudaSuccess || n <= 0) { cudaGetLastError(); n = num_sms / 4; }
+    max_clusters = n < num_sms / 4 ? n : num_sms / 4;
+    if (getenv("SAMRS_VERBOSE")) fprintf(stderr, "gemm_tc4<%d>: %d clusters of 4 co-resident\n", BN, max_clusters);
+  }
+  const int grid = 4 * (supers < max_clusters ? supers : max_clusters);
+  SAMRS_CUDA_OK(launch_pdl(gemm_tc4_kernel<BN, OH, ACT>, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, tA, tB, tC, p));
+  count_launch();
+  return 0;
+}
+
+#endif
+
+#ifndef SAMRS_GELU_EPI_WARPS
+#define SAMRS_GELU_EPI_WARPS 8       // epilogue warps of the fp16 + GELU pair kernel; 12 (three column groups) measured the same (profiles/r02_gemm_epi12_ab.txt)
+#endif
+constexpr int GELU_EPI_WARPS = SAMRS_GELU_EPI_WARPS;
+constexpr int SK_MAX_TILES = 1024;   // counters the engine owns (two ints per tile)
+#ifndef SAMRS_SK_BN
+#define SAMRS_SK_BN 0                // N tile of the stream-K GEMMs on the ViT-H shapes (256 / 160); 0 = tile schedule, which measured faster
+#endif
+constexpr int SK_BN = SAMRS_SK_BN;
+
+#ifdef SAMRS_EXPERIMENTS
+template <int BN>
+static int launch_gemm2_sk_inst(const CUtensorMap& tA, const CUtensorMap& tB, const CUtensorMap& tC, const GemmParams& p, int grid, cudaStream_t st) {
+  using Cfg = Gemm2Cfg<BN>;
+  SAMRS_TRY(opt_in_smem(gemm_tc2_sk_kernel<BN>, Cfg::kSmemBytes));
+  SAMRS_CUDA_OK(launch_pdl(gemm_tc2_sk_kernel<BN>, dim3(grid), dim3(GEMM_THREADS), Cfg::kSmemBytes, st, tA, tB, tC, p));
+  count_launch();
+  return 0;
+}
+#endif
 
 // model of one tile's duration in SM clocks: tensor-pipe time vs the L2->SM feed (~50 B/clk/SM measured)
 // (feed rates fitted to tools/gemm_sweep.py on a B200: ~80 B/clk/SM for the 1-CTA kernel, ~52 for the CTA-pair kernel)
@@ -202,14 +251,20 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   if (p.K % 8 != 0 || lda % 8 != 0 || ldb % 8 != 0) SAMRS_FAIL("gemm: K and leading dimensions must be multiples of 8");
   // force_bn: 0 = choose; 128/160/224/256 = 1-CTA kernel with that N tile; 1000 + bn = CTA-pair kernel;
   // 2000 + bn = cluster of two 1-CTA tiles sharing B through TMA multicast
+  // 3000 + bn = CTA-pair kernel with the stream-K schedule (fp32 accumulate epilogue only)
   int bn = force_bn % 1000;
-  bool pair = force_bn >= 1000 && force_bn < 2000;
-  bool mcast = force_bn >= 2000;
+  // 4000 + bn = two CTA pairs per cluster sharing the B tile through TMA multicast (gemm_tc4_kernel)
+  bool pair = (force_bn >= 1000 && force_bn < 2000) || force_bn >= 3000;
+  bool mcast = force_bn >= 2000 && force_bn < 3000;
+  bool streamk = force_bn >= 3000 && force_bn < 4000;
+  bool quad = force_bn >= 4000;
   if (force_bn == 0 && p.M == 4096 && p.batch == 1 && (p.N == 1280 || p.N == 3840 || p.N == 5120) && num_sms == 148) {
     // ViT-H shapes: measured best configurations (profiles/r01_gemm_sweep_v4.json): the CTA-pair kernel everywhere
     // (it halves the B bytes each SM pulls from L2; 1-CTA tiles are feed-bound once the issue loop is tight)
     bn = (p.N == 1280) ? 160 : 224;
     pair = true;
+    // proj / lin2 (out += ...): stream-K over 256-wide tiles, see gemm_tc2_sk_kernel
+    if (SK_BN > 0 && p.N == 1280 && p.accumulate && !out_half && act == 0 && p.sk_flags != nullptr) { bn = SK_BN; streamk = true; }
 #ifdef SAMRS_EXPERIMENTS
     // experiment hook: SAMRS_BN="n1280,n3840,n5120" with force_bn codes (e.g. "160,224,256" = 1-CTA kernels)
     static int env_bn[3] = {-1, 0, 0};
@@ -244,7 +299,7 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   if (a_map_rank3) tA = *a_map_rank3;
   else SAMRS_TRY(make_tmap_2d(&tA, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, GEMM_BK, GEMM_BM));
   if (mcast && (((p.M + 127) / 128) % 2 != 0 || (num_sms & 1) || a_map_rank3)) mcast = false;
-  SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t((pair || mcast) ? bn / 2 : bn)));
+  SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t(quad ? bn / 4 : ((pair || mcast) ? bn / 2 : bn))));
   CUtensorMap tC;
   SAMRS_TRY(make_tmap_out(&tC, p.out, out_half, uint64_t(p.N), uint64_t(p.M), uint64_t(p.batch), uint64_t(p.ldc), uint64_t(p.out_batch_stride), 32));
   CUtensorMap tC16 = tC;
@@ -254,13 +309,49 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   }
   if (p.res != nullptr && (p.ldr % 4 != 0)) SAMRS_FAIL("gemm: residual leading dimension must be a multiple of 4");
   const int tiles = p.tiles_m * p.tiles_n * p.batch;
+#ifndef SAMRS_EXPERIMENTS
+  if (quad || streamk) SAMRS_FAIL("gemm: the stream-K and cluster-of-4 schedules exist in -DSAMRS_EXPERIMENTS builds only");
+#else
+  if (quad) {
+    if (p.batch != 1 || a_map_rank3 || bn % 32 != 0 || (num_sms & 3)) SAMRS_FAIL("gemm: the cluster-of-4 kernel takes plain 2-D problems and 32-column tile multiples");
+    const int supers = ((p.tiles_m + 1) / 2) * p.tiles_n;
+#define SAMRS_GEMM4_CASE(BN_)                                                                       \
+  if (bn == BN_) {                                                                                  \
+    if (out_half && act == 0) return launch_gemm4_inst<BN_, true, 0>(tA, tB, tC, p, supers, num_sms, stream);     \
+    if (out_half && act == 1) return launch_gemm4_inst<BN_, true, 1>(tA, tB, tC, p, supers, num_sms, stream);     \
+    if (!out_half && act == 0) return launch_gemm4_inst<BN_, false, 0>(tA, tB, tC, p, supers, num_sms, stream);   \
+    SAMRS_FAIL("gemm: unsupported epilogue");                                                       \
+  }
+    SAMRS_GEMM4_CASE(224)
+    SAMRS_GEMM4_CASE(160)
+    SAMRS_GEMM4_CASE(256)
+#undef SAMRS_GEMM4_CASE
+    SAMRS_FAIL("gemm: unsupported N tile");
+  }
+  if (streamk) {
+    const int pairs = num_sms / 2, num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+    const bool ok = !out_half && act == 0 && p.accumulate && p.batch == 1 && !a_map_rank3 && p.sk_flags != nullptr && bn % 32 == 0 &&
+                    p.res == nullptr && tiles <= SK_MAX_TILES && tiles >= pairs && (long(tiles) * num_kb) / pairs >= num_kb;
+    if (!ok) {
+      if (force_bn >= 3000) SAMRS_FAIL("gemm: stream-K needs the fp32 accumulate epilogue, engine counters and at least one tile per CTA pair");
+      streamk = false;                                   // shape does not qualify: tile schedule of the same kernel family
+    }
+  }
+  if (streamk) {
+    const int grid2 = 2 * (num_sms / 2);
+    if (bn == 256) return launch_gemm2_sk_inst<256>(tA, tB, tC, p, grid2, stream);
+    if (bn == 160) return launch_gemm2_sk_inst<160>(tA, tB, tC, p, grid2, stream);
+    if (bn == 128) return launch_gemm2_sk_inst<128>(tA, tB, tC, p, grid2, stream);
+    SAMRS_FAIL("gemm: unsupported stream-K N tile");
+  }
+#endif
   if (pair) {
     const int pairs = num_sms / 2;
     const int grid2 = 2 * (tiles < pairs ? tiles : pairs);
 #define SAMRS_GEMM2_CASE(BN_)                                                                       \
   if (bn == BN_) {                                                                                  \
     if (out_half && act == 0) return launch_gemm2_inst<BN_, true, 0>(tA, tB, tC, tC16, p, grid2, stream);     \
-    if (out_half && act == 1) return launch_gemm2_inst<BN_, true, 1>(tA, tB, tC, tC16, p, grid2, stream);     \
+    if (out_half && act == 1) return launch_gemm2_inst<BN_, true, 1, GELU_EPI_WARPS>(tA, tB, tC, tC16, p, grid2, stream);     \
     if (!out_half && act == 0) return launch_gemm2_inst<BN_, false, 0>(tA, tB, tC, tC16, p, grid2, stream);   \
     SAMRS_FAIL("gemm: unsupported epilogue");                                                       \
   }
@@ -896,6 +987,8 @@ static int alloc_activations(Engine* e) {
   SAMRS_TRY(e->alloc(&e->src0A, T * 768));
   e->ctx.splitk_ws_floats = size_t(8) * 1024 * 2048;
   SAMRS_TRY(e->alloc(&e->ctx.splitk_ws, e->ctx.splitk_ws_floats));
+  SAMRS_TRY(e->alloc(&e->ctx.sk_flags, size_t(2) * SK_MAX_TILES));
+  SAMRS_CUDA_OK(cudaMemset(e->ctx.sk_flags, 0, size_t(2) * SK_MAX_TILES * sizeof(int)));
   return 0;
 }
 
@@ -952,6 +1045,7 @@ static int gemm_enc(Engine* e, cudaStream_t st, const __half* A, int lda, const 
   p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.tiles_m = p.tiles_n = 0;
   p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 0.f; p.dbg = nullptr; p.dbg_mode = 0; p.accumulate = accumulate;
+  p.sk_flags = e->ctx.sk_flags;
   ProfScope ps(PC_GEMM, st);
   return launch_gemm_tc(A, lda, W, K, p, out_half, act, e->num_sms, st, 0);
 }
@@ -1646,6 +1740,7 @@ int samrs_test_gemm(void* engine, const void* A, const void* B, int M, int N, in
   p.dbg_mode = g_gemm_mode;
   p.accumulate = 0;
   if (res != nullptr && res == out && !out_half) { p.res = nullptr; p.accumulate = 1; }   // in-place residual -> TMA reduce-add
+  p.sk_flags = e->ctx.sk_flags;
   return set_err(e, launch_gemm_tc(static_cast<const __half*>(A), K, static_cast<const __half*>(B), K, p, out_half != 0, act_gelu, e->num_sms,
                                    static_cast<cudaStream_t>(stream), force_bn));
 }

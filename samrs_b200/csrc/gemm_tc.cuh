@@ -36,6 +36,8 @@ struct GemmParams {
   const float* hyper = nullptr;   // [B][hyper_nm][32]
   float* low = nullptr;           // [B][hyper_nm][256][256] low-res mask logits
   int hyper_nm = 0;
+  // stream-K schedule (gemm_tc2_sk_kernel): two zero-initialised counters per output tile, owned by the engine
+  int* sk_flags = nullptr;
 };
 // Pipeline traces and the "remove one stage" experiments of tools/gemm_trace.py exist only in builds with
 // -DSAMRS_EXPERIMENTS (build.sh exp -> libsamrs_b200_exp.so); the product library compiles them away.
@@ -137,6 +139,51 @@ __device__ __forceinline__ void gemm_epilogue_warp_half(const GemmParams& p, con
     if (elect_one()) {                           // same lane every time (full-warp mask): bulk groups are per thread
       tma_store_3d(tmC, buf, n0 + c * 32, row0, bt);
       if (two) tma_store_3d(tmC, buf + 2048, n0 + (c + 1) * 32, row0, bt);
+      tma_store_commit();
+    }
+  }
+}
+
+// fp16-output epilogue for the kernels that run twelve epilogue warps (lin1 + GELU: with eight warps the ~17 instructions per
+// element of bias + erf-GELU + pack made the epilogue, not the main loop, set the tile period: 9.3 k clk against 8 k,
+// profiles/r01_gemm_trace_v5.txt).  Three column groups of at most three chunks; a warp owns 4 KiB of staging = two 2 KiB
+// blocks that alternate, one 32-column chunk per TMA store.
+template <int BN, int ACT>
+__device__ __forceinline__ void gemm_epilogue_warp_half1(const GemmParams& p, const CUtensorMap* tmC, uint32_t t_addr, int row0, int n0,
+                                                         float oscale, uint8_t* stage /*4 KiB*/, uint32_t& nstaged, int lane,
+                                                         const float (&bias_r)[(BN + 31) / 32], int chunk_begin, int chunk_end) {
+  static_assert(BN % 32 == 0, "fp16-output tiles are whole 32-column chunks");
+  constexpr int NCH = BN / 32;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    if (c < chunk_begin || c >= chunk_end) continue;
+    if (n0 + c * 32 >= p.N) break;
+    uint32_t v[32];
+    tmem_ld32(t_addr + uint32_t(c * 32), v);
+    uint8_t* buf = stage + (nstaged & 1) * 2048;
+    ++nstaged;
+    if (elect_one()) tma_store_wait_read<1>();   // the block staged two chunks ago has been read by the TMA unit
+    __syncwarp();
+    tc_wait_ld();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        f[i] = fmaf(__uint_as_float(v[8 * j + i]), oscale, __shfl_sync(0xffffffffu, bias_r[c], 8 * j + i));
+        if (ACT == 1) f[i] = gelu_erf(f[i]);
+      }
+      __half2 h0 = __floats2half2_rn(f[0], f[1]), h1 = __floats2half2_rn(f[2], f[3]);
+      __half2 h2 = __floats2half2_rn(f[4], f[5]), h3 = __floats2half2_rn(f[6], f[7]);
+      uint4 pk;
+      pk.x = *reinterpret_cast<uint32_t*>(&h0); pk.y = *reinterpret_cast<uint32_t*>(&h1);
+      pk.z = *reinterpret_cast<uint32_t*>(&h2); pk.w = *reinterpret_cast<uint32_t*>(&h3);
+      *reinterpret_cast<uint4*>(buf + lane * 64 + j * 16) = pk;
+    }
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (elect_one()) {
+      tma_store_3d(tmC, buf, n0 + c * 32, row0, 0);
       tma_store_commit();
     }
   }

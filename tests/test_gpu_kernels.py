@@ -20,6 +20,17 @@ def eng80():
     return Engine("vit_t80", "cuda:0")
 
 
+def _gemm(eng, *args, **kw):
+    """Engine.test_gemm; schedules that live in the -DSAMRS_EXPERIMENTS build only (force_bn >= 3000: stream-K, cluster of four)
+    skip the test when the product library is loaded (run them with SAMRS_LIB=libsamrs_b200_exp.so)."""
+    try:
+        return eng.test_gemm(*args, **kw)
+    except RuntimeError as e:
+        if "SAMRS_EXPERIMENTS" in str(e):
+            pytest.skip("schedule compiled into libsamrs_b200_exp.so only")
+        raise
+
+
 def _rand(shape, seed, scale=1.0, dtype=torch.float16):
     g = torch.Generator(device="cpu").manual_seed(seed)
     return (torch.randn(shape, generator=g) * scale).to(dtype).cuda()
@@ -48,18 +59,67 @@ def test_gemm_fp32_out_bias_residual(eng64, M, N, K, bn):
 
 
 @pytest.mark.parametrize("M,N,K,bn", [(4096, 1280, 1280, 0), (4096, 1280, 5120, 1160), (300, 200, 192, 160), (4096, 1280, 1280, 1256),
-                                         (4096, 1280, 5120, 1144), (512, 304, 128, 1144)])
+                                         (4096, 1280, 5120, 1144), (512, 304, 128, 1144),
+                                         # stream-K schedule of the pair kernel (force_bn = 3000 + N tile): split tiles, ragged M / N, short K
+                                         (4096, 1280, 1280, 3256), (4096, 1280, 5120, 3256), (4096, 1280, 5120, 3160), (4096, 1280, 1280, 3128),
+                                         (4000, 1300, 320, 3256), (4096, 1280, 64, 3160)])
 def test_gemm_inplace_residual_reduce_add(eng64, M, N, K, bn):
     """x += A B^T + bias with x both residual and output: the epilogue issues TMA reduce-add stores."""
     A, B = _rand((M, K), 31), _rand((N, K), 32, 1.0 / math.sqrt(K))
     bias = _rand((N,), 33, dtype=torch.float32)
     x = _rand((M, N), 34, dtype=torch.float32)
     ref = x + A.float() @ B.float().t() + bias
-    out = eng64.test_gemm(A, B, out_half=False, bias=bias, res=x, force_bn=bn, out=x)
+    out = _gemm(eng64, A, B, out_half=False, bias=bias, res=x, force_bn=bn, out=x)
     torch.cuda.synchronize()
     assert out is x
     err = (x - ref).abs().max().item()
     assert err < 2e-3, f"max err {err}"
+
+
+@pytest.mark.parametrize("K,bn", [(1280, 3256), (5120, 3256), (5120, 3160), (5120, 0)])
+def test_gemm_stream_k_is_deterministic(eng64, K, bn):
+    """A tile cut between two CTA pairs receives `head` then `tail` in a fixed order: repeated launches (which also re-arm the
+    per-tile counters) give the same bits, and they agree with the tile-scheduled kernel to fp32 re-association."""
+    M, N = 4096, 1280
+    A, B = _rand((M, K), 41), _rand((N, K), 42, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 43, dtype=torch.float32)
+    x0 = _rand((M, N), 44, dtype=torch.float32)
+    outs = []
+    for _ in range(4):
+        x = x0.clone()
+        _gemm(eng64, A, B, out_half=False, bias=bias, res=x, force_bn=bn, out=x)
+        outs.append(x)
+    torch.cuda.synchronize()
+    for o in outs[1:]:
+        assert torch.equal(o, outs[0])
+    y = x0.clone()
+    eng64.test_gemm(A, B, out_half=False, bias=bias, res=y, force_bn=1160, out=y)
+    torch.cuda.synchronize()
+    assert (y - outs[0]).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("M,N,K,bn,half,gelu", [
+    (4096, 3840, 1280, 4224, True, False), (4096, 5120, 1280, 4224, True, True), (4096, 1280, 5120, 4160, False, False),
+    (4096, 1280, 1280, 4160, False, False), (1024, 448, 128, 4224, True, False), (700, 520, 200, 4256, False, False),
+    (512, 224, 64, 4224, False, False)])
+def test_gemm_cluster_of_four_shares_b_by_multicast(eng64, M, N, K, bn, half, gelu):
+    """Two CTA pairs per cluster, B tile loaded once per cluster (force_bn = 4000 + N tile): same results as the pair kernel,
+    including a ragged last super-tile (M = 700: the second pair's rows are out of range) and a single super-tile."""
+    A, B = _rand((M, K), 51), _rand((N, K), 52, 1.0 / math.sqrt(K))
+    bias = _rand((N,), 53, dtype=torch.float32)
+    ref = A.float() @ B.float().t() + bias
+    if gelu:
+        ref = torch.nn.functional.gelu(ref)
+    if half:
+        out = _gemm(eng64, A, B, out_half=True, bias=bias, gelu=gelu, force_bn=bn)
+        torch.cuda.synchronize()
+        assert (out.float() - ref).abs().max().item() < 6e-3
+    else:
+        x = _rand((M, N), 54, dtype=torch.float32)
+        ref = ref + x
+        _gemm(eng64, A, B, out_half=False, bias=bias, res=x, force_bn=bn, out=x)
+        torch.cuda.synchronize()
+        assert (x - ref).abs().max().item() < 2e-3
 
 
 @pytest.mark.parametrize("M,N,K,gelu", [(4096, 3840, 1280, False), (4096, 5120, 1280, True), (384, 520, 136, True)])

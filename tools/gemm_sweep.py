@@ -26,8 +26,20 @@ for name, (M, N, K, half, gelu) in shapes.items():
     res[f"{name}/cublas"] = (round(us, 1), round(2.0 * M * N * K / us / 1e6, 1))
     print(f"{name:11s} cuBLAS   : {us:7.1f} us  {2.0*M*N*K/us/1e6:7.1f} TFLOP/s", flush=True)
     for c in cfgs:
-        if half and c % 1000 % 32 != 0:
-            continue                        # tiles that are not a multiple of 32 wide have the fp32 epilogue only
+        if half and (c % 1000 % 32 != 0 or 3000 <= c < 4000):
+            continue                        # fp32-epilogue-only variants: tiles not a multiple of 32 wide, stream-K (3000 + bn)
+        if 3000 <= c < 4000:                # stream-K exists for the in-place reduce-add epilogue only
+            x = torch.randn(M, N, device="cuda")
+            for _ in range(3): eng.test_gemm(A, B, out_half=False, bias=bias, gelu=gelu, force_bn=c, res=x, out=x)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(20): eng.test_gemm(A, B, out_half=False, bias=bias, gelu=gelu, force_bn=c, res=x, out=x)
+            b.record(); torch.cuda.synchronize()
+            us = a.elapsed_time(b) / 20 * 1000
+            res[f"{name}/{c}"] = (round(us, 1), round(2.0 * M * N * K / us / 1e6, 1))
+            print(f"{name:11s} cfg {c:5d} [inplace]: {us:7.1f} us  {2.0*M*N*K/us/1e6:7.1f} TFLOP/s", flush=True)
+            continue
         for _ in range(3):
             eng.test_gemm(A, B, out_half=half, bias=bias, res=r, gelu=gelu, force_bn=c)
         torch.cuda.synchronize()
