@@ -297,7 +297,9 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
   p.tiles_n = (p.N + bn - 1) / bn;
   CUtensorMap tA, tB;
   if (a_map_rank3) tA = *a_map_rank3;
-  else SAMRS_TRY(make_tmap_2d(&tA, A, uint64_t(p.K), uint64_t(p.M), uint64_t(lda) * 2, GEMM_BK, GEMM_BM));
+  else SAMRS_TRY(make_tmap_2d(&tA, A, uint64_t(p.a_wrap_kb > 0 ? p.a_wrap_kb * GEMM_BK : p.K), uint64_t(p.M), uint64_t(lda) * 2, GEMM_BK, GEMM_BM));
+  if (p.a_wrap_kb > 0 && (quad || streamk || mcast || a_map_rank3 || p.K != 3 * (p.a_wrap_kb / 2) * GEMM_BK || (p.a_wrap_kb & 1)))
+    SAMRS_FAIL("gemm: a wrapped A operand is [hi | lo] of a 3-term split GEMM (K' = 3K, K a multiple of 64) on the plain tile schedules");
   if (mcast && (((p.M + 127) / 128) % 2 != 0 || (num_sms & 1) || a_map_rank3)) mcast = false;
   SAMRS_TRY(make_tmap_2d(&tB, B, uint64_t(p.K), uint64_t(p.N), uint64_t(ldb) * 2, GEMM_BK, uint32_t(quad ? bn / 4 : ((pair || mcast) ? bn / 2 : bn))));
   CUtensorMap tC;
@@ -452,6 +454,10 @@ struct Engine {
   struct GraphEntry { cudaGraphExec_t exec = nullptr; int launches = 0; int eager_runs = 0; };
   bool graphs_enabled = true;
   cudaStream_t cap_stream = nullptr;
+  // second stream of the decode body: the token-side chain of the next layer and the up-scaling LayerNorm run beside the
+  // image-side kernels they do not depend on (fork / join through these events; inside a capture they become parallel graph branches)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork[2] = {nullptr, nullptr}, ev_join[2] = {nullptr, nullptr};
   GraphEntry enc_graph;
   std::unordered_map<uint64_t, GraphEntry> dec_graphs;
   void drop_graphs() {
@@ -489,7 +495,7 @@ struct Engine {
   // per-image decoder cache
   float *src0, *KVQ0;                  // KVQ0 [4096][384] = layer-0 [K (t2i) | V (t2i) | Q (i2t)] of the image tokens
   float *b_kvq0 = nullptr, *R_kvq0 = nullptr;                      // their concatenated biases / positional terms
-  __half *wd_kvq0 = nullptr, *src0A = nullptr;                     // split-fp16 [Wk ; Wv ; Wq] (384 x 768) and src0 (4096 x 768)
+  __half *wd_kvq0 = nullptr, *src0A = nullptr;                     // split-fp16 [Wk ; Wv ; Wq] (384 x 768 = [hi | hi | lo]) and src0 (4096 x 512 = [hi | lo])
   float* pp_full = nullptr;            // postprocess scratch for non-1024 sizes
   struct ResizeTab { int in, out, ksize; int* bounds; int* kk; std::vector<int> h_bounds, h_kk; unsigned long long used; };
   std::vector<ResizeTab> resize_tabs;   // Pillow tap tables per (input size, output size), built on first use; LRU of 32
@@ -506,10 +512,10 @@ struct Engine {
   float* d_t2i_part = nullptr;         // [cap][8][16][8][18] key-chunk partials of the token->image attention
   // decoder scratch (sized for dec_cap prompts)
   int dec_cap = 0;
-  float *d_tok0 = nullptr, *d_q = nullptr, *d_tmp256a = nullptr, *d_tmp256b = nullptr, *d_tmp256c = nullptr, *d_tmp256d = nullptr;
+  float *d_tok0 = nullptr, *d_q = nullptr, *d_qkv = nullptr /*[BT][768] self-attention q | k | v*/, *d_tmp256d = nullptr;
   float *d_tmp128a = nullptr, *d_tmp128b = nullptr, *d_tmp128c = nullptr, *d_mlp = nullptr;
   float *d_keys = nullptr, *d_P = nullptr, *d_hyper = nullptr, *d_hy_a = nullptr, *d_hy_b = nullptr, *d_iou_all = nullptr, *d_low = nullptr;
-  __half *d_keysA = nullptr, *d_ioA = nullptr, *d_up1 = nullptr;   // d_up1: split-fp16 GELU(LN(ConvT1)) [cap*16384][192]
+  __half *d_keysA = nullptr, *d_ioA = nullptr, *d_up1 = nullptr;   // split-fp16 [hi | lo] operands; d_up1: GELU(LN(ConvT1)) [cap*16384][128]
   int mask_cap = 0;                    // mask-prompt path scratch (per-prompt layer-0 operands), allocated on first use
   float *d_Kp = nullptr, *d_Vp = nullptr, *d_Qp = nullptr, *d_src = nullptr;
 
@@ -775,16 +781,24 @@ static int build_reltab(Engine* e, cudaStream_t st, const float* rph, const floa
 }
 
 static int load_dec_attn(Engine* e, cudaStream_t st, const SrcMap& m, const std::string& pre, int internal, DecAttn* a) {
+  // q | k | v projection weights and biases are stored back to back ([3 * internal][256], [3 * internal])
   const float* s;
   a->internal = internal;
-  SAMRS_TRY(need(m, pre + ".q_proj.weight", int64_t(internal) * 256, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(internal) * 256, &a->wq));
-  SAMRS_TRY(need(m, pre + ".q_proj.bias", internal, &s));                  SAMRS_TRY(copy_f32(e, st, s, internal, &a->bq));
-  SAMRS_TRY(need(m, pre + ".k_proj.weight", int64_t(internal) * 256, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(internal) * 256, &a->wk));
-  SAMRS_TRY(need(m, pre + ".k_proj.bias", internal, &s));                  SAMRS_TRY(copy_f32(e, st, s, internal, &a->bk));
-  SAMRS_TRY(need(m, pre + ".v_proj.weight", int64_t(internal) * 256, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(internal) * 256, &a->wv));
-  SAMRS_TRY(need(m, pre + ".v_proj.bias", internal, &s));                  SAMRS_TRY(copy_f32(e, st, s, internal, &a->bv));
-  SAMRS_TRY(need(m, pre + ".out_proj.weight", int64_t(internal) * 256, &s)); SAMRS_TRY(copy_f32(e, st, s, int64_t(internal) * 256, &a->wo));
-  SAMRS_TRY(need(m, pre + ".out_proj.bias", 256, &s));                     SAMRS_TRY(copy_f32(e, st, s, 256, &a->bo));
+  const int64_t nw = int64_t(internal) * 256;
+  float *wbase = nullptr, *bbase = nullptr;
+  SAMRS_TRY(e->alloc(&wbase, size_t(3 * nw)));
+  SAMRS_TRY(e->alloc(&bbase, size_t(3 * internal)));
+  a->wq = wbase; a->wk = wbase + nw; a->wv = wbase + 2 * nw;
+  a->bq = bbase; a->bk = bbase + internal; a->bv = bbase + 2 * internal;
+  const char* names[3] = {".q_proj", ".k_proj", ".v_proj"};
+  for (int i = 0; i < 3; ++i) {
+    SAMRS_TRY(need(m, pre + names[i] + ".weight", nw, &s));
+    SAMRS_CUDA_OK(cudaMemcpyAsync(wbase + i * nw, s, size_t(nw) * 4, cudaMemcpyDeviceToDevice, st));
+    SAMRS_TRY(need(m, pre + names[i] + ".bias", internal, &s));
+    SAMRS_CUDA_OK(cudaMemcpyAsync(bbase + i * internal, s, size_t(internal) * 4, cudaMemcpyDeviceToDevice, st));
+  }
+  SAMRS_TRY(need(m, pre + ".out_proj.weight", nw, &s)); SAMRS_TRY(copy_f32(e, st, s, nw, &a->wo));
+  SAMRS_TRY(need(m, pre + ".out_proj.bias", 256, &s));  SAMRS_TRY(copy_f32(e, st, s, 256, &a->bo));
   return 0;
 }
 static int load_pair(Engine* e, cudaStream_t st, const SrcMap& m, const std::string& pre, int64_t n, float** w, float** b) {
@@ -984,7 +998,7 @@ static int alloc_activations(Engine* e) {
   SAMRS_TRY(e->alloc(&e->feat_nchw, T * 256));
   SAMRS_TRY(e->alloc(&e->src0, T * 256));
   SAMRS_TRY(e->alloc(&e->KVQ0, T * 384));
-  SAMRS_TRY(e->alloc(&e->src0A, T * 768));
+  SAMRS_TRY(e->alloc(&e->src0A, T * 512));
   e->ctx.splitk_ws_floats = size_t(8) * 1024 * 2048;
   SAMRS_TRY(e->alloc(&e->ctx.splitk_ws, e->ctx.splitk_ws_floats));
   SAMRS_TRY(e->alloc(&e->ctx.sk_flags, size_t(2) * SK_MAX_TILES));
@@ -1000,9 +1014,7 @@ static int ensure_decoder_scratch(Engine* e, int B) {
   const size_t c = cap, TT = 16;
   e->release(&e->d_tok0); SAMRS_TRY(e->alloc(&e->d_tok0, c * TT * 256));
   e->release(&e->d_q); SAMRS_TRY(e->alloc(&e->d_q, c * TT * 256));
-  e->release(&e->d_tmp256a); SAMRS_TRY(e->alloc(&e->d_tmp256a, c * TT * 256));
-  e->release(&e->d_tmp256b); SAMRS_TRY(e->alloc(&e->d_tmp256b, c * TT * 256));
-  e->release(&e->d_tmp256c); SAMRS_TRY(e->alloc(&e->d_tmp256c, c * TT * 256));
+  e->release(&e->d_qkv); SAMRS_TRY(e->alloc(&e->d_qkv, c * TT * 768));
   e->release(&e->d_tmp256d); SAMRS_TRY(e->alloc(&e->d_tmp256d, c * TT * 256));
   e->release(&e->d_tmp128a); SAMRS_TRY(e->alloc(&e->d_tmp128a, c * TT * 128));
   e->release(&e->d_tmp128b); SAMRS_TRY(e->alloc(&e->d_tmp128b, c * TT * 128));
@@ -1011,9 +1023,9 @@ static int ensure_decoder_scratch(Engine* e, int B) {
   e->release(&e->d_t2i_part); SAMRS_TRY(e->alloc(&e->d_t2i_part, c * 8 * 16 * 8 * 18));
   e->release(&e->d_keys); SAMRS_TRY(e->alloc(&e->d_keys, c * 4096 * 256));
   e->release(&e->d_P); SAMRS_TRY(e->alloc(&e->d_P, c * 4096 * 512));
-  e->release(&e->d_keysA); SAMRS_TRY(e->alloc(&e->d_keysA, c * 4096 * 768));
-  e->release(&e->d_ioA); SAMRS_TRY(e->alloc(&e->d_ioA, c * 4096 * 384));
-  e->release(&e->d_up1); SAMRS_TRY(e->alloc(&e->d_up1, c * 16384 * 192));
+  e->release(&e->d_keysA); SAMRS_TRY(e->alloc(&e->d_keysA, c * 4096 * 512));
+  e->release(&e->d_ioA); SAMRS_TRY(e->alloc(&e->d_ioA, c * 4096 * 256));
+  e->release(&e->d_up1); SAMRS_TRY(e->alloc(&e->d_up1, c * 16384 * 128));
   e->release(&e->d_hyper); SAMRS_TRY(e->alloc(&e->d_hyper, c * 4 * 32));
   e->release(&e->d_hy_a); SAMRS_TRY(e->alloc(&e->d_hy_a, c * 256));
   e->release(&e->d_hy_b); SAMRS_TRY(e->alloc(&e->d_hy_b, c * 256));
@@ -1118,25 +1130,32 @@ static int gemm_dec(Engine* e, cudaStream_t st, const __half* A3, const __half* 
   GemmParams p;
   p.M = M; p.N = N; p.K = K3; p.out = out; p.ldc = ldc; p.bias = bias; p.res = res; p.ldr = ldr; p.res_mod = res_mod;
   p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f; p.dbg = nullptr; p.dbg_mode = 0; p.accumulate = accumulate;
-  return launch_gemm_tc(A3, K3, W3, K3, p, false, 0, e->num_sms, st, 0);
+  // A = [hi | lo] with 2K = 2/3 K' columns; the GEMM reads the hi block a second time for its third term
+  const int K2 = K3 / 3 * 2;
+  if (K3 % 192 != 0) SAMRS_FAIL("split GEMM: K must be a multiple of 64");
+  p.a_wrap_kb = K2 / GEMM_BK;
+  return launch_gemm_tc(A3, K2, W3, K3, p, false, 0, e->num_sms, st, 0);
 }
 
-static int add2(cudaStream_t st, const float* a, const float* b, float* out, size_t n) {
-  // out = a + b (elementwise, same shape; out may be a)
-  add_out_kernel<<<unsigned((n + 255) / 256), 256, 0, st>>>(a, b, out, n);
+// LayerNorm of the token rows in place plus `with_pe = normed + pe` for the next attention's q / k input (transformer.py:161-179)
+static int ln_tokens(cudaStream_t st, float* x, const float* g, const float* b, const float* pe, float* with_pe, int rows) {
+  ln256_tok_kernel<<<(rows + 7) / 8, 256, 0, st>>>(x, g, b, 1e-5f, pe, with_pe, rows);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return 0;
 }
 
-static int token_attention(Engine* e, cudaStream_t st, const DecAttn& a, const float* q_in, const float* k_in, const float* v_in,
+static int token_attention(Engine* e, cudaStream_t st, const DecAttn& a, const float* qk_in, const float* v_in,
                            int BT, int T, int B, float* out256 /*projected*/, const float* residual) {
-  // self-attention on tokens (internal dim 256)
-  SAMRS_TRY(sgemm(st, q_in, 256, a.wq, 256, e->d_tmp256a, 256, a.bq, nullptr, 0, 0, BT, 256, 256, 0));
-  SAMRS_TRY(sgemm(st, k_in, 256, a.wk, 256, e->d_tmp256b, 256, a.bk, nullptr, 0, 0, BT, 256, 256, 0));
-  SAMRS_TRY(sgemm(st, v_in, 256, a.wv, 256, e->d_tmp256c, 256, a.bv, nullptr, 0, 0, BT, 256, 256, 0));
+  // self-attention on tokens (internal dim 256); the three projections land side by side as [BT][q | k | v].  They stay three
+  // launches of 56 blocks: one GEMM over the concatenated weight rows (168 blocks x 66 KB of shared memory at once) made the
+  // decoder 27 us faster in isolation and the two-stream step 1.5 % SLOWER - every SM it touches is closed to the other tile's
+  // persistent 220 KB GEMM blocks for its duration (profiles/r02_decoder_ab.txt)
+  SAMRS_TRY(sgemm(st, qk_in, 256, a.wq, 256, e->d_qkv, 768, a.bq, nullptr, 0, 0, BT, 256, 256, 0));
+  SAMRS_TRY(sgemm(st, qk_in, 256, a.wk, 256, e->d_qkv + 256, 768, a.bk, nullptr, 0, 0, BT, 256, 256, 0));
+  SAMRS_TRY(sgemm(st, v_in, 256, a.wv, 256, e->d_qkv + 512, 768, a.bv, nullptr, 0, 0, BT, 256, 256, 0));
   const size_t smem = (size_t(3) * T * 256 + 8 * T * T) * 4;
-  tok_self_attn_kernel<<<B, 256, smem, st>>>(e->d_tmp256a, e->d_tmp256b, e->d_tmp256c, e->d_tmp256d, T);
+  tok_self_attn_kernel<<<B, 256, smem, st>>>(e->d_qkv, e->d_qkv + 256, e->d_qkv + 512, 768, e->d_tmp256d, T);
   SAMRS_CUDA_OK(cudaGetLastError());
   count_launch();
   return sgemm(st, e->d_tmp256d, 256, a.wo, 256, out256, 256, a.bo, residual, 256, 0, BT, 256, 256, 0);
@@ -1183,8 +1202,25 @@ static int decode_chunk(Engine* e, cudaStream_t st, const float* boxes, const fl
     p.tiles_m = p.tiles_n = 0; p.batch = 1; p.a_rank3 = 0; p.out_batch_stride = 0; p.out_scale = 1.0f / 256.0f; p.dbg = nullptr; p.dbg_mode = 0;
     p.accumulate = 0;
     p.hyper = e->d_hyper; p.low = lowres_out; p.hyper_nm = NM;
-    SAMRS_TRY(launch_gemm_tc(e->d_up1, 192, e->wd_up2, 192, p, false, 3, e->num_sms, st, 128));
+    p.a_wrap_kb = 2;                                   // d_up1 rows are [hi(64) | lo(64)]
+    SAMRS_TRY(launch_gemm_tc(e->d_up1, 128, e->wd_up2, 192, p, false, 3, e->num_sms, st, 128));
   }
+  return 0;
+}
+
+#ifndef SAMRS_DEC_FORK
+#define SAMRS_DEC_FORK 3             // bit 0: layer 1's token chain beside layer 0's image-side tail; bit 1: up-scaling LayerNorm beside the heads
+#endif
+constexpr int DEC_FORK = SAMRS_DEC_FORK;
+// work issued to `side_stream` after fork_side(i) runs beside what follows on `st` until join_side(i)
+static int fork_side(Engine* e, cudaStream_t st, int i) {
+  SAMRS_CUDA_OK(cudaEventRecord(e->ev_fork[i], st));
+  SAMRS_CUDA_OK(cudaStreamWaitEvent(e->side_stream, e->ev_fork[i], 0));
+  return 0;
+}
+static int join_side(Engine* e, cudaStream_t st, int i) {
+  SAMRS_CUDA_OK(cudaEventRecord(e->ev_join[i], e->side_stream));
+  SAMRS_CUDA_OK(cudaStreamWaitEvent(st, e->ev_join[i], 0));
   return 0;
 }
 
@@ -1209,29 +1245,23 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
   }
 
   float* queries = e->d_q;
-  float* qpl = e->d_tmp256d;          // queries + query_pe (scratch; token_attention uses a..d before we need it again)
+  float* qpl = e->d_tmp256d;          // queries + query_pe, written by the token LayerNorms (also the self-attention's output scratch)
   const int M4 = B * 4096;
   const unsigned ln_blocks = unsigned((size_t(M4) * 32 + 255) / 256);
   for (int layer = 0; layer < 2; ++layer) {
     const DecLayer& L = e->dl[layer];
-    // (1) token self-attention (transformer.py:155-161)
+    // (1) token self-attention (transformer.py:155-161) and (2)'s query projection (:164-165).  Layer 1's were issued to the side
+    //     stream at the end of layer 0 (below): they only need the tokens, not the image-side update that was still running
     if (layer == 0) {
-      SAMRS_TRY(token_attention(e, st, L.self_attn, e->d_tok0, e->d_tok0, e->d_tok0, BT, T, B, queries, nullptr));
-    } else {
-      float* qpe = e->d_mlp;            // reuse the MLP scratch as a [BT,256] temporary
-      SAMRS_TRY(add2(st, queries, e->d_tok0, qpe, size_t(BT) * 256));
-      SAMRS_TRY(token_attention(e, st, L.self_attn, qpe, qpe, queries, BT, T, B, queries, queries));
-    }
-    SAMRS_TRY((ln_rows<float, 0>(st, queries, 256, L.n1w, L.n1b, 1e-5f, queries, 256, BT, 256)));
-    // (2) tokens -> image (transformer.py:164-168)
-    SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
-    SAMRS_TRY(sgemm(st, qpl, 256, L.t2i.wq, 256, e->d_tmp128a, 128, L.t2i.bq, nullptr, 0, 0, BT, 128, 256, 0));
-    if (layer == 0) {
-      t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128a, K0, V0, ld0, kv_stride, e->d_t2i_part, T);
+      SAMRS_TRY(token_attention(e, st, L.self_attn, e->d_tok0, e->d_tok0, BT, T, B, queries, nullptr));
+      SAMRS_TRY(ln_tokens(st, queries, L.n1w, L.n1b, e->d_tok0, qpl, BT));
+      SAMRS_TRY(sgemm(st, qpl, 256, L.t2i.wq, 256, e->d_tmp128c, 128, L.t2i.bq, nullptr, 0, 0, BT, 128, 256, 0));
+      t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128c, K0, V0, ld0, kv_stride, e->d_t2i_part, T);
     } else {
       // K | V | Q(i2t) projections of the per-prompt image tokens in one tensor-core GEMM
       SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p1, M4, 384, 768, e->d_P, 384, e->bias_p1, e->R1, 384, 4096));
-      t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 384, size_t(4096) * 384, e->d_t2i_part, T);
+      if ((DEC_FORK & 1) != 0) SAMRS_TRY(join_side(e, st, 0));
+      t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128c, e->d_P, e->d_P + 128, 384, size_t(4096) * 384, e->d_t2i_part, T);
     }
     t2i_combine_kernel<<<(B * 8 * T * 16 + 255) / 256, 256, 0, st>>>(e->d_t2i_part, e->d_tmp128b, B, T, T2I_CHUNKS);
     SAMRS_CUDA_OK(cudaGetLastError());
@@ -1241,11 +1271,22 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
     // (3) token MLP (transformer.py:171-173)
     SAMRS_TRY(sgemm(st, queries, 256, L.m1w, 256, e->d_mlp, 2048, L.m1b, nullptr, 0, 0, BT, 2048, 256, 1));
     SAMRS_TRY(sgemm(st, e->d_mlp, 2048, L.m2w, 2048, queries, 256, L.m2b, queries, 256, 0, BT, 256, 2048, 0));
-    SAMRS_TRY((ln_rows<float, 0>(st, queries, 256, L.n3w, L.n3b, 1e-5f, queries, 256, BT, 256)));
+    SAMRS_TRY(ln_tokens(st, queries, L.n3w, L.n3b, e->d_tok0, qpl, BT));
     // (4) image -> tokens (transformer.py:176-180)
-    SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
     SAMRS_TRY(sgemm(st, qpl, 256, L.i2t.wk, 256, e->d_tmp128a, 128, L.i2t.bk, nullptr, 0, 0, BT, 128, 256, 0));
     SAMRS_TRY(sgemm(st, queries, 256, L.i2t.wv, 256, e->d_tmp128b, 128, L.i2t.bv, nullptr, 0, 0, BT, 128, 256, 0));
+    if (layer == 0) {
+      // the tokens are final for this layer: layer 1's self-attention, norm1 and t2i query projection (6 small, latency-bound
+      // kernels) run on the side stream while the image-side kernels below stream their 100+ MB.  q = k = queries + pe is the
+      // `qpl` norm3 just wrote (the attention kernel overwrites that scratch only after the q | k projection has read it);
+      // the side chain touches queries, qpl, d_qkv and d_tmp128c, none of which the image side reads
+      cudaStream_t sd = (DEC_FORK & 1) != 0 ? e->side_stream : st;
+      const DecLayer& L1 = e->dl[1];
+      if ((DEC_FORK & 1) != 0) SAMRS_TRY(fork_side(e, st, 0));
+      SAMRS_TRY(token_attention(e, sd, L1.self_attn, qpl, queries, BT, T, B, queries, queries));
+      SAMRS_TRY(ln_tokens(sd, queries, L1.n1w, L1.n1b, e->d_tok0, qpl, BT));
+      SAMRS_TRY(sgemm(sd, qpl, 256, L1.t2i.wq, 256, e->d_tmp128c, 128, L1.t2i.bq, nullptr, 0, 0, BT, 128, 256, 0));
+    }
     if (layer == 0)
       i2t_attn_kernel<<<dim3(4096 / I2T_TOK_PER_BLOCK, B), 256, size_t(2) * T * 8 * I2T_HP * 4, st>>>(Qi0, ld0, kv_stride, e->d_tmp128a, e->d_tmp128b, e->d_ioA, T);
     else
@@ -1265,13 +1306,22 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
   // final tokens -> image attention (transformer.py:99-104); its K | V projections share one GEMM with ConvT1
   {
     const DecAttn& a = e->final_attn;
-    SAMRS_TRY(add2(st, queries, e->d_tok0, qpl, size_t(BT) * 256));
-    SAMRS_TRY(sgemm(st, qpl, 256, a.wq, 256, e->d_tmp128a, 128, a.bq, nullptr, 0, 0, BT, 128, 256, 0));
+    // q = queries + pe is the `qpl` layer 1's norm3 left behind
+    SAMRS_TRY(sgemm(st, qpl, 256, a.wq, 256, e->d_tmp128c, 128, a.bq, nullptr, 0, 0, BT, 128, 256, 0));
     SAMRS_TRY(gemm_dec(e, st, e->d_keysA, e->wd_p2, M4, 512, 768, e->d_P, 512, e->bias_p2, e->R2, 512, 4096));
-    t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128a, e->d_P, e->d_P + 128, 512, size_t(4096) * 512, e->d_t2i_part, T);
+    t2i_attn_kernel<<<dim3(B, 8, T2I_CHUNKS), 32 * T, 0, st>>>(e->d_tmp128c, e->d_P, e->d_P + 128, 512, size_t(4096) * 512, e->d_t2i_part, T);
     t2i_combine_kernel<<<(B * 8 * T * 16 + 255) / 256, 256, 0, st>>>(e->d_t2i_part, e->d_tmp128b, B, T, T2I_CHUNKS);
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch(2);
+    // up-scaling: the ConvT1 columns of P2 -> LN2d + GELU per 64-channel group -> split fp16 operand of the ConvT2 GEMM.  It only
+    // needs P2: one full-GPU streaming kernel that runs on the side stream beside the ~10 small, latency-bound kernels of the
+    // output projection, final norm and the hyper-network / IoU heads
+    const bool fork_tail = (DEC_FORK & 2) != 0;
+    cudaStream_t s64 = fork_tail ? e->side_stream : st;
+    if (fork_tail) SAMRS_TRY(fork_side(e, st, 1));
+    ln64_gelu_split_kernel<<<unsigned((size_t(M4) * 4 * 16 + 255) / 256), 256, 0, s64>>>(e->d_P, 512, 256, e->up_lnw, e->up_lnb, M4, e->d_up1);
+    SAMRS_CUDA_OK(cudaGetLastError());
+    count_launch();
     SAMRS_TRY(sgemm(st, e->d_tmp128b, 128, a.wo, 128, queries, 256, a.bo, queries, 256, 0, BT, 256, 128, 0));
     SAMRS_TRY((ln_rows<float, 0>(st, queries, 256, e->nfw, e->nfb, 1e-5f, queries, 256, BT, 256)));
   }
@@ -1289,10 +1339,8 @@ static int decode_body(Engine* e, cudaStream_t st, bool has_mask, int B, int T, 
   // last layer restricted to the returned slice: rows m_first .. m_first+NM-1 of the (4,256) weight
   SAMRS_TRY(sgemm(st, e->d_hy_b, 256, e->iou_head.w[2] + m_first * 256, 256, e->d_iou_all, NM, e->iou_head.b[2] + m_first, nullptr, 0, 0, B, NM,
                   256, 0));
-  // upscaling: ConvT1 columns of P2 -> LN2d+GELU per 64-channel group (in place); ConvT2+GELU+hyper product follows outside
-  ln64_gelu_split_kernel<<<unsigned((size_t(M4) * 4 * 16 + 255) / 256), 256, 0, st>>>(e->d_P, 512, 256, e->up_lnw, e->up_lnb, M4, e->d_up1);
-  SAMRS_CUDA_OK(cudaGetLastError());
-  count_launch();
+  // the ConvT2 + GELU + hyper-network product (decode_chunk) needs both branches
+  if ((DEC_FORK & 2) != 0) SAMRS_TRY(join_side(e, st, 1));
   return 0;
 }
 
@@ -1332,7 +1380,11 @@ int samrs_create(int device, int embed_dim, int depth, int num_heads, const int*
   e->D = embed_dim; e->depth = depth; e->heads = num_heads; e->hd = hd;
   e->global_idx.assign(global_idx, global_idx + n_global);
   e->num_sms = prop.multiProcessorCount;
-  if (alloc_activations(e) != 0 || cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  bool side_ok = cudaStreamCreateWithFlags(&e->side_stream, cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < 2 && side_ok; ++i)
+    side_ok = cudaEventCreateWithFlags(&e->ev_fork[i], cudaEventDisableTiming) == cudaSuccess &&
+              cudaEventCreateWithFlags(&e->ev_join[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!side_ok || alloc_activations(e) != 0 || cudaStreamCreateWithFlags(&e->cap_stream, cudaStreamNonBlocking) != cudaSuccess) {
     samrs_destroy(e);
     return 1;
   }
@@ -1720,6 +1772,11 @@ void samrs_destroy(void* engine) {
   cudaDeviceSynchronize();
   e->drop_graphs();
   if (e->cap_stream) cudaStreamDestroy(e->cap_stream);
+  if (e->side_stream) cudaStreamDestroy(e->side_stream);
+  for (int i = 0; i < 2; ++i) {
+    if (e->ev_fork[i]) cudaEventDestroy(e->ev_fork[i]);
+    if (e->ev_join[i]) cudaEventDestroy(e->ev_join[i]);
+  }
   for (void* p : e->allocs) cudaFree(p);
   for (void* p : e->weight_allocs) cudaFree(p);
   for (auto& r : e->ctx.prof.recs) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }

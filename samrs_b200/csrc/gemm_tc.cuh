@@ -36,6 +36,9 @@ struct GemmParams {
   const float* hyper = nullptr;   // [B][hyper_nm][32]
   float* low = nullptr;           // [B][hyper_nm][256][256] low-res mask logits
   int hyper_nm = 0;
+  // 3-term split-fp16 GEMMs (mask decoder): A is stored as [hi | lo] (2K columns) and its k-blocks >= a_wrap_kb are read again
+  // from the start, i.e. the operand behaves as [hi | lo | hi] without the third copy ever being written or fetched from HBM
+  int a_wrap_kb = 0;
   // stream-K schedule (gemm_tc2_sk_kernel): two zero-initialised counters per output tile, owned by the engine
   int* sk_flags = nullptr;
 };
@@ -441,8 +444,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (elect_one()) mbar_arrive(&full[stage]);
           } else if (elect_one()) {
             mbar_expect_tx(&full[stage], Cfg::kStageBytes);
-            if (p.a_rank3) tma_load_3d(sa, &tmA, &full[stage], kb * GEMM_BK, bt, m0);
-            else tma_load_2d(sa, &tmA, &full[stage], kb * GEMM_BK, m0);
+            const int ka = (p.a_wrap_kb > 0 && kb >= p.a_wrap_kb) ? kb - p.a_wrap_kb : kb;
+            if (p.a_rank3) tma_load_3d(sa, &tmA, &full[stage], ka * GEMM_BK, bt, m0);
+            else tma_load_2d(sa, &tmA, &full[stage], ka * GEMM_BK, m0);
             if (CM == 2) tma_load_2d_mcast(sb + crank * (BN / 2) * 128, &tmB, &full[stage], kb * GEMM_BK, n0 + crank * (BN / 2), 0x3);
             else tma_load_2d(sb, &tmB, &full[stage], kb * GEMM_BK, n0);
           }

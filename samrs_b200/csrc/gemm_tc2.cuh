@@ -95,7 +95,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__
           const uint32_t lead_full = mapa_u32(&full[stage], 0);
           if (elect_one()) {
             if (rank == 0) mbar_expect_tx(&full[stage], 2 * Cfg::kStageBytes);
-            tma_load_2d_pair(sa, &tmA, lead_full, kb * GEMM_BK, m0);
+            tma_load_2d_pair(sa, &tmA, lead_full, ((p.a_wrap_kb > 0 && kb >= p.a_wrap_kb) ? kb - p.a_wrap_kb : kb) * GEMM_BK, m0);
             tma_load_2d_pair(sb, &tmB, lead_full, kb * GEMM_BK, n0);
           }
           __syncwarp();

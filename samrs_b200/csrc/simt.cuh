@@ -159,6 +159,49 @@ __global__ void ln_rows_kernel(const float* __restrict__ in, int ld_in, const fl
   }
 }
 
+// Token rows of the mask decoder (C = 256): x = LayerNorm(x) in place and `with_pe` = x + pe, the q / k input of the next
+// attention (transformer.py:161-179) - the arithmetic of ln_rows_kernel<float, 0, 2> followed by a plain add, one warp per row.
+__global__ void __launch_bounds__(256) ln256_tok_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        float eps, const float* __restrict__ pe, float* __restrict__ with_pe, int rows) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  float4* xr = reinterpret_cast<float4*>(x + size_t(row) * 256);
+  float4 v[2];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    v[i] = xr[lane + 32 * i];
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / 256.0f;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / 256.0f + eps);
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int k = lane + 32 * i;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + k);
+    const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + k);
+    const float4 p = reinterpret_cast<const float4*>(pe + size_t(row) * 256)[k];
+    float4 y;
+    y.x = (v[i].x - mean) * rstd * g.x + b.x;
+    y.y = (v[i].y - mean) * rstd * g.y + b.y;
+    y.z = (v[i].z - mean) * rstd * g.z + b.z;
+    y.w = (v[i].w - mean) * rstd * g.w + b.w;
+    xr[k] = y;
+    reinterpret_cast<float4*>(with_pe + size_t(row) * 256)[k] = make_float4(y.x + p.x, y.y + p.y, y.z + p.z, y.w + p.w);
+  }
+}
+
 // fp32 -> fp16 cast of a contiguous buffer (n multiple of 4)
 __global__ void cast_f32_f16_kernel(const float* __restrict__ in, __half* __restrict__ out, size_t n4) {
   const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -379,11 +422,6 @@ __global__ void splitk_reduce_kernel(const SgemmParams p, const float* __restric
   p.C[size_t(m) * p.ldc + n] = v;
 }
 
-// out = a + b (queries + query_pe of the two-way blocks, transformer.py:164,176; out may alias a)
-__global__ void add_out_kernel(const float* a, const float* __restrict__ b, float* out, size_t n) {
-  const size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i < n) out[i] = a[i] + b[i];
-}
 
 // ------------------------------------------------------------------------------------------------
 // Prompt encoder (SA/modeling/prompt_encoder.py:73-100,128-173,190-219) + decoder token assembly
@@ -538,7 +576,7 @@ __global__ void mask_embed_src_kernel(const MaskEmbedParams p, int B) {
 // ------------------------------------------------------------------------------------------------
 // (1) token self-attention: q,k,v [B][T][256] already projected, 8 heads x 32.  One block per prompt.
 __global__ void tok_self_attn_kernel(const float* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
-                                     float* __restrict__ out, int T) {
+                                     int ld /*row pitch of q, k, v*/, float* __restrict__ out, int T) {
   extern __shared__ float sm[];
   float* sq = sm;
   float* sk = sq + T * 256;
@@ -546,9 +584,10 @@ __global__ void tok_self_attn_kernel(const float* __restrict__ q, const float* _
   float* sc = sv + T * 256;               // [8][T][T]
   const int b = blockIdx.x;
   for (int i = threadIdx.x; i < T * 256; i += blockDim.x) {
-    sq[i] = q[size_t(b) * T * 256 + i];
-    sk[i] = k[size_t(b) * T * 256 + i];
-    sv[i] = v[size_t(b) * T * 256 + i];
+    const size_t g = (size_t(b) * T + (i >> 8)) * ld + (i & 255);
+    sq[i] = q[g];
+    sk[i] = k[g];
+    sv[i] = v[g];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 8 * T * T; i += blockDim.x) {
@@ -695,9 +734,9 @@ __device__ __forceinline__ void split_f16(float v, __half& hi, __half& lo) {
 }
 
 // src0 = image embedding + no_mask_embed (mask_decoder.py:136 with the dense "no mask" prompt, prompt_encoder.py:165-168), written
-// as fp32 (residual of the first image-side update) and as the split-fp16 A operand [hi | lo | hi] of the layer-0 projection GEMM
+// as fp32 (residual of the first image-side update) and as the split-fp16 A operand [hi | lo] of the layer-0 projection GEMM
 __global__ void add_rowvec_split_kernel(const float* __restrict__ a, const float* __restrict__ vec, float* __restrict__ out,
-                                        __half* __restrict__ out_split /*[rows][3 * C]*/, int rows, int C) {
+                                        __half* __restrict__ out_split /*[rows][2 * C]*/, int rows, int C) {
   const size_t i4 = size_t(blockIdx.x) * blockDim.x + threadIdx.x;          // 4 consecutive channels
   if (i4 * 4 >= size_t(rows) * C) return;
   const int r = int(i4 * 4 / C), c = int(i4 * 4 % C);
@@ -708,19 +747,18 @@ __global__ void add_rowvec_split_kernel(const float* __restrict__ a, const float
   __half hi[4], lo[4];
 #pragma unroll
   for (int t = 0; t < 4; ++t) split_f16(y[t], hi[t], lo[t]);
-  __half* o = out_split + size_t(r) * 3 * C + c;
+  __half* o = out_split + size_t(r) * 2 * C + c;
   *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
   *reinterpret_cast<uint2*>(o + C) = *reinterpret_cast<const uint2*>(lo);
-  *reinterpret_cast<uint2*>(o + 2 * C) = *reinterpret_cast<const uint2*>(hi);
 }
 
 // (3) image -> token cross attention: Q rows of `ldq` floats, prompt stride q_bstride (0 = shared); k,v [B][T][128].
-//     One thread per (image token, head): the 8 threads of a token read its 512-byte Q row and write the three 256-byte
+//     One thread per (image token, head): the 8 threads of a token read its 512-byte Q row and write the two 256-byte
 //     segments of its output row together, so every warp-wide access is four whole rows.  The prompt's k,v sit in shared
 //     memory with a head pitch of 20 floats: the eight heads a warp touches at once then fall into eight different bank
 //     groups (with the natural pitch of 16 they collide 4-way, which made the first per-head version 2.4x slower than the
 //     one-thread-per-token kernel it replaced).  The result feeds the out_proj tensor-core GEMM and is written directly
-//     as the split-fp16 operand [B*4096][hi(128) | lo(128) | hi(128)].
+//     as the split-fp16 operand [B*4096][hi(128) | lo(128)].
 constexpr int I2T_HP = 20;                 // floats per (token, head) slice in shared memory
 constexpr int I2T_TOK_PER_BLOCK = 128;     // image tokens per block (4 passes of 32 tokens x 8 heads)
 __global__ void __launch_bounds__(256)
@@ -780,18 +818,16 @@ i2t_attn_kernel(const float* __restrict__ Q, int ldq, size_t q_bstride, const fl
     __half hi[16], lo[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) split_f16(acc[c] * inv, hi[c], lo[c]);
-    __half* o = out_split + (size_t(b) * 4096 + token) * 384 + h * 16;
+    __half* o = out_split + (size_t(b) * 4096 + token) * 256 + h * 16;
     reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<uint4*>(hi)[0];
     reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<uint4*>(hi)[1];
     reinterpret_cast<uint4*>(o + 128)[0] = reinterpret_cast<uint4*>(lo)[0];
     reinterpret_cast<uint4*>(o + 128)[1] = reinterpret_cast<uint4*>(lo)[1];
-    reinterpret_cast<uint4*>(o + 256)[0] = reinterpret_cast<uint4*>(hi)[0];
-    reinterpret_cast<uint4*>(o + 256)[1] = reinterpret_cast<uint4*>(hi)[1];
   }
 }
 
 // LayerNorm over 256 channels (decoder norm4, eps 1e-5) writing the fp32 result (optional) and its split-fp16
-// form [hi(256) | lo(256) | hi(256)] for the following tensor-core GEMMs.  One warp per row.
+// form [hi(256) | lo(256)] for the following tensor-core GEMMs.  One warp per row.
 __global__ void ln256_split_kernel(const float* __restrict__ in, const float* __restrict__ gamma, const float* __restrict__ beta,
                                    float eps, float* __restrict__ out_f32, __half* __restrict__ out_split, int rows) {
   const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -820,20 +856,19 @@ __global__ void ln256_split_kernel(const float* __restrict__ in, const float* __
     if (out_f32) reinterpret_cast<float4*>(out_f32 + size_t(row) * 256)[k] = make_float4(y0, y1, y2, y3);
     __half hi[4], lo[4];
     split_f16(y0, hi[0], lo[0]); split_f16(y1, hi[1], lo[1]); split_f16(y2, hi[2], lo[2]); split_f16(y3, hi[3], lo[3]);
-    __half* o = out_split + size_t(row) * 768 + 4 * k;
+    __half* o = out_split + size_t(row) * 512 + 4 * k;
     *reinterpret_cast<uint2*>(o) = *reinterpret_cast<uint2*>(hi);
     *reinterpret_cast<uint2*>(o + 256) = *reinterpret_cast<uint2*>(lo);
-    *reinterpret_cast<uint2*>(o + 512) = *reinterpret_cast<uint2*>(hi);
   }
 }
 
 
 // LayerNorm2d(64, eps 1e-6) + GELU of output_upscaling (SA/modeling/mask_decoder.py:54-57, common.py:31-43) on the 64-channel
 // groups base[row * ld + off + g * 64 + c], g < 4 (the ConvT1 columns of the fused projection GEMM); half a warp per group.
-// The result leaves as the 3-term split-fp16 A operand [hi | lo | hi] of the tensor-core ConvTranspose2 GEMM: row
-// (token * 4 + group) of out, 192 halves (precision recipe).
+// The result leaves as the split-fp16 A operand [hi | lo] of the 3-term tensor-core ConvTranspose2 GEMM (which reads the hi block
+// twice): row (token * 4 + group) of out, 128 halves (precision recipe).
 __global__ void ln64_gelu_split_kernel(const float* __restrict__ base, int ld, int off, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, int rows, __half* __restrict__ out /*[rows*4][192]*/) {
+                                       const float* __restrict__ beta, int rows, __half* __restrict__ out /*[rows*4][128]*/) {
   const int gidx = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;       // (row, group)
   const int l16 = threadIdx.x & 15;
   if (gidx >= rows * 4) return;
@@ -854,12 +889,11 @@ __global__ void ln64_gelu_split_kernel(const float* __restrict__ base, int ld, i
   __half hi[4], lo[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) split_f16(y[i], hi[i], lo[i]);
-  __half* o = out + size_t(gidx) * 192 + l16 * 4;
+  __half* o = out + size_t(gidx) * 128 + l16 * 4;
   *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
   *reinterpret_cast<uint2*>(o + 64) = *reinterpret_cast<const uint2*>(lo);
-  *reinterpret_cast<uint2*>(o + 128) = *reinterpret_cast<const uint2*>(hi);
 }
-// weight [N][K] fp32 -> split-fp16 [N][3K] = scale * [hi | hi | lo], matching activations stored [hi | lo | hi]
+// weight [N][K] fp32 -> split-fp16 [N][3K] = scale * [hi | hi | lo], matching activations [hi | lo | hi] (stored [hi | lo], hi read twice)
 __global__ void split_weight_kernel(const float* __restrict__ w, int N, int K, float scale, __half* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N * K) return;
