@@ -588,6 +588,10 @@ static int run_graphed(Engine* e, Engine::GraphEntry& ge, cudaStream_t st, F&& b
   return 0;
 }
 
+#ifndef SAMRS_SGEMM_NARROW
+#define SAMRS_SGEMM_NARROW 1
+#endif
+constexpr bool SGEMM_NARROW = SAMRS_SGEMM_NARROW != 0;
 static void* g_attn_dbg = nullptr;            // device buffer for attention pipeline traces (tools only)
 // ------------------------------------------------------------------ small launch helpers
 static int sgemm(cudaStream_t st, const float* A, int lda, const float* W, int ldw, float* C, int ldc, const float* bias,
@@ -602,9 +606,15 @@ static int sgemm(cudaStream_t st, const float* A, int lda, const float* W, int l
     if (splits > 1 && !(ws && size_t(M) * N * splits <= t_ctx->splitk_ws_floats)) SAMRS_FAIL("sgemm: split-K workspace too small");
     const int kps = ((K / splits + 15) / 16) * 16;
     if (kps > SGT_KMAX || kps * splits < K) SAMRS_FAIL("sgemm: K does not split into panels of at most 256");
-    SAMRS_TRY(opt_in_smem(sgemm_small_kernel, SGT_SMEM));
-    dim3 grid((M + 31) / 32, (N + 31) / 32, splits);
-    sgemm_small_kernel<<<grid, 128, SGT_SMEM, st>>>(p, kps, splits > 1 ? ws : nullptr);
+    // 32 x 32 output tiles, or 32 x 16 when that would leave most of the GPU without a block (N = 128 / 256 with a few hundred rows)
+    const bool narrow = SGEMM_NARROW && ((M + 31) / 32) * ((N + 31) / 32) * splits < 148 && N % 16 == 0;
+    if (narrow) {
+      SAMRS_TRY(opt_in_smem(sgemm_small_kernel<16>, SGT_SMEM));
+      sgemm_small_kernel<16><<<dim3((M + 31) / 32, N / 16, splits), 128, SGT_SMEM, st>>>(p, kps, splits > 1 ? ws : nullptr);
+    } else {
+      SAMRS_TRY(opt_in_smem(sgemm_small_kernel<32>, SGT_SMEM));
+      sgemm_small_kernel<32><<<dim3((M + 31) / 32, (N + 31) / 32, splits), 128, SGT_SMEM, st>>>(p, kps, splits > 1 ? ws : nullptr);
+    }
     SAMRS_CUDA_OK(cudaGetLastError());
     count_launch();
     if (splits > 1) {

@@ -341,13 +341,15 @@ sgemm_tn_kernel(const SgemmParams p) {
 constexpr int SGT_KMAX = 256;
 constexpr int SGT_PITCH = SGT_KMAX + 4;
 constexpr int SGT_SMEM = 2 * 32 * SGT_PITCH * 4;
+template <int TN /*output columns per block: 32, or 16 when 32-wide tiles would leave most SMs without a block*/>
 __global__ void __launch_bounds__(128)
 sgemm_small_kernel(const SgemmParams p, int k_per_split, float* __restrict__ ws /*[splits][M][N] or null*/) {
   extern __shared__ __align__(16) float sgt_smem[];
   float* As = sgt_smem;
   float* Ws = sgt_smem + 32 * SGT_PITCH;
   const int tid = threadIdx.x;
-  const int m0 = blockIdx.x * 32, n0 = blockIdx.y * 32;
+  constexpr int NJ = TN / 8;
+  const int m0 = blockIdx.x * 32, n0 = blockIdx.y * TN;
   const int kbeg = blockIdx.z * k_per_split;
   const int kn = min(p.K, kbeg + k_per_split) - kbeg;          // <= 256, multiple of 16 (host)
   const int k4n = kn >> 2;
@@ -361,31 +363,33 @@ sgemm_small_kernel(const SgemmParams p, int k_per_split, float* __restrict__ ws 
     } else {
       *reinterpret_cast<float4*>(da) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    if (wr < p.N) {
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dw)), "l"(p.W + size_t(wr) * p.ldw + kbeg + 4 * c4) : "memory");
-    } else {
-      *reinterpret_cast<float4*>(dw) = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (r < TN) {
+      if (wr < p.N) {
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dw)), "l"(p.W + size_t(wr) * p.ldw + kbeg + 4 * c4) : "memory");
+      } else {
+        *reinterpret_cast<float4*>(dw) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   __syncthreads();
   const int tm = tid >> 3, tn = tid & 7;                        // rows tm, tm + 16; columns tn, tn + 8, tn + 16, tn + 24
-  float acc[2][4];
+  float acc[2][NJ];
 #pragma unroll
   for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < NJ; ++j) acc[i][j] = 0.f;
 #pragma unroll 4
   for (int c4 = 0; c4 < k4n; ++c4) {
-    float4 a[2], w[4];
+    float4 a[2], w[NJ];
 #pragma unroll
     for (int i = 0; i < 2; ++i) a[i] = *reinterpret_cast<const float4*>(As + (tm + 16 * i) * SGT_PITCH + 4 * c4);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = *reinterpret_cast<const float4*>(Ws + (tn + 8 * j) * SGT_PITCH + 4 * c4);
+    for (int j = 0; j < NJ; ++j) w[j] = *reinterpret_cast<const float4*>(Ws + (tn + 8 * j) * SGT_PITCH + 4 * c4);
 #pragma unroll
     for (int i = 0; i < 2; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
+      for (int j = 0; j < NJ; ++j) {
         float v = acc[i][j];
         v = fmaf(a[i].x, w[j].x, v); v = fmaf(a[i].y, w[j].y, v); v = fmaf(a[i].z, w[j].z, v); v = fmaf(a[i].w, w[j].w, v);
         acc[i][j] = v;
@@ -396,7 +400,7 @@ sgemm_small_kernel(const SgemmParams p, int k_per_split, float* __restrict__ ws 
     const int m = m0 + tm + 16 * i;
     if (m >= p.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < NJ; ++j) {
       const int n = n0 + tn + 8 * j;
       if (n >= p.N) continue;
       float v = acc[i][j];

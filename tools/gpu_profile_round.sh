@@ -16,3 +16,8 @@ cap attn "attn_tc2" 6 2
 cap epi "upsample4|ln_rows_stream|rle_pack|rle_scan|coco_string" 0 8
 cap dec "t2i_attn|i2t_attn|sgemm_small|gemm_tc_kernel<128, false, 3|ln256_split|ln64_gelu" 0 8
 ls -la gpurun_out | head -30; du -sh gpurun_out
+# the same launch list without flushing caches between kernels (per-kernel times as they are inside a step)
+timeout 300 ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --cache-control none --csv \
+  --log-file gpurun_out/launches_warm.csv python tools/profile_step.py > gpurun_out/ncu_warm.log 2>&1
+python tools/summarize_launches.py gpurun_out/launches_warm.csv gpurun_out/launches_warm_summary.csv | head -5
+du -sh gpurun_out
