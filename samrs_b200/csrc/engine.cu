@@ -116,7 +116,7 @@ struct LaunchCtx {
   Profiler prof;
   float* splitk_ws = nullptr;                     // split-K partial sums of the token-side SGEMMs
   size_t splitk_ws_floats = 0;
-  int* sk_flags = nullptr;                        // stream-K tile counters of the encoder GEMMs (zero between launches)
+  int* sk_flags = nullptr;                        // experiments build only: stream-K tile counters (zero between launches)
   std::unordered_set<const void*> smem_opted;     // kernels whose dynamic-smem limit was raised on this engine's device
   bool capturing = false;                         // a CUDA graph is being captured: no events, no attribute calls
   bool pdl = true;                                // programmatic dependent launch for the kernels that support it
@@ -218,11 +218,13 @@ static int launch_gemm4_inst(const CUtensorMap& tA, const CUtensorMap& tB, const
 #define SAMRS_GELU_EPI_WARPS 8       // epilogue warps of the fp16 + GELU pair kernel; 12 (three column groups) measured the same (profiles/r02_gemm_epi12_ab.txt)
 #endif
 constexpr int GELU_EPI_WARPS = SAMRS_GELU_EPI_WARPS;
+#ifdef SAMRS_EXPERIMENTS
 constexpr int SK_MAX_TILES = 1024;   // counters the engine owns (two ints per tile)
 #ifndef SAMRS_SK_BN
 #define SAMRS_SK_BN 0                // N tile of the stream-K GEMMs on the ViT-H shapes (256 / 160); 0 = tile schedule, which measured faster
 #endif
 constexpr int SK_BN = SAMRS_SK_BN;
+#endif
 
 #ifdef SAMRS_EXPERIMENTS
 template <int BN>
@@ -263,9 +265,9 @@ int launch_gemm_tc(const __half* A, int lda, const __half* B, int ldb, const Gem
     // (it halves the B bytes each SM pulls from L2; 1-CTA tiles are feed-bound once the issue loop is tight)
     bn = (p.N == 1280) ? 160 : 224;
     pair = true;
-    // proj / lin2 (out += ...): stream-K over 256-wide tiles, see gemm_tc2_sk_kernel
-    if (SK_BN > 0 && p.N == 1280 && p.accumulate && !out_half && act == 0 && p.sk_flags != nullptr) { bn = SK_BN; streamk = true; }
 #ifdef SAMRS_EXPERIMENTS
+    // -DSAMRS_SK_BN=160|256: proj / lin2 (out += ...) on the stream-K schedule, see gemm_tc2_sk_kernel
+    if (SK_BN > 0 && p.N == 1280 && p.accumulate && !out_half && act == 0 && p.sk_flags != nullptr) { bn = SK_BN; streamk = true; }
     // experiment hook: SAMRS_BN="n1280,n3840,n5120" with force_bn codes (e.g. "160,224,256" = 1-CTA kernels)
     static int env_bn[3] = {-1, 0, 0};
     if (env_bn[0] < 0) {
@@ -1011,8 +1013,10 @@ static int alloc_activations(Engine* e) {
   SAMRS_TRY(e->alloc(&e->src0A, T * 512));
   e->ctx.splitk_ws_floats = size_t(8) * 1024 * 2048;
   SAMRS_TRY(e->alloc(&e->ctx.splitk_ws, e->ctx.splitk_ws_floats));
+#ifdef SAMRS_EXPERIMENTS
   SAMRS_TRY(e->alloc(&e->ctx.sk_flags, size_t(2) * SK_MAX_TILES));
   SAMRS_CUDA_OK(cudaMemset(e->ctx.sk_flags, 0, size_t(2) * SK_MAX_TILES * sizeof(int)));
+#endif
   return 0;
 }
 
