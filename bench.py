@@ -23,6 +23,8 @@ The default run also measures pts5 and tiny64 briefly and reports them under `ex
               gray / color PNG + instance pickle written by a thread pool (`samrs_b200.stream.run`).
 `roofline`  : the tcgen05 encoder GEMMs (dominant kernel): algorithmic FLOPs per launch / mean launch time, measured with CUDA events
               on the launching stream inside a timed pass with one tile in flight (samrs_profile).
+              `roofline.attn_window / attn_global / whole_step`: the same reading for the attention kernels and for the whole step
+              (algorithmic FLOPs of a tile x tiles/s), against the same measured peak.
 `epilogue`  : the fused HBM-bound epilogue kernels (upsample + threshold + paint): algorithmic bytes / CUDA-event time vs the HBM peak.
 """
 from __future__ import annotations
@@ -65,6 +67,36 @@ def gemm_flops_per_encode(g) -> float:
     f += g.depth * 2.0 * T * D * (3 * D + D + 4 * D + 4 * D)
     f += 2.0 * T * D * 256 + 2.0 * T * 2304 * 256
     return f
+
+
+def attention_flops_per_encode(g) -> tuple:
+    """Algorithmic FLOPs of QK^T + PV per encode, (windowed blocks, global blocks): 2 GEMMs x 2 x queries x keys x D per block;
+    a windowed query sees its 14 x 14 window (115.09 / 343.60 GFLOP for ViT-H)."""
+    D, T = g.embed_dim, 4096
+    n_glob = len(g.global_attn_indexes)
+    return (g.depth - n_glob) * 4.0 * T * 196 * D, n_glob * 4.0 * T * T * D
+
+
+DECODER_GFLOP_PER_PROMPT = {5: 3.590, 7: 3.623, 10: 3.672}       # SURVEY.md A.7 (tokens per prompt: 5 + sparse prompt tokens)
+
+
+def roofline_extras(g, prof, prof_steps, masks_per_s_per_gpu, prompts, tokens_per_prompt, peak_tf) -> dict:
+    """The other two readings north_star asks for, against the same measured tensor peak as `roofline`: the attention kernels
+    (CUDA-event time of every attention launch, one tile in flight) and the whole step (algorithmic FLOPs of a tile x tiles/s)."""
+    out = {}
+    fw, fg = attention_flops_per_encode(g)
+    for key, fl in (("attn_window", fw), ("attn_global", fg)):
+        ms, cnt = prof.get(key, (0.0, 0))
+        if ms > 0 and cnt > 0:
+            tf = fl * prof_steps / (ms / 1000.0) / 1e12
+            out[key] = {"achieved": tf, "frac": tf / peak_tf, "unit": "TFLOP/s", "ms_per_step": ms / prof_steps, "launches_per_step": cnt / prof_steps}
+    dec = DECODER_GFLOP_PER_PROMPT.get(tokens_per_prompt)
+    if g.name == "vit_h" and dec is not None:
+        tile_gflop = 5641.8 + prompts * dec                            # SURVEY.md 8(d): 179.9 GFLOP per mask at 32 boxes
+        tf = masks_per_s_per_gpu / prompts * tile_gflop / 1e3
+        out["whole_step"] = {"achieved": tf, "frac": tf / peak_tf, "unit": "TFLOP/s", "gflop_per_tile": tile_gflop,
+                             "note": "algorithmic FLOPs of encoder + decoder x tiles per second per GPU (resident `value`)"}
+    return out
 
 
 def measured_peaks():
@@ -514,6 +546,11 @@ def run_ours(args):
                                           "graph_replay_ms_per_step: the same single-stream step as the engine normally runs it"},
         "clocks": clocks,
     }
+    try:                                                              # readings derived from numbers above: never fatal
+        tokens = {"box": 7, "pts5": 10, "tiny": 7}.get(rig.wl["kind"])
+        line["roofline"].update(roofline_extras(rig.g, prof, prof_steps, value / world, n, tokens, peak_tf))
+    except Exception as ex:
+        line["roofline"]["extras_error"] = repr(ex)[:200]
     if not args.no_extra:
         k2 = max(4, args.steps // 2)
         try:

@@ -63,3 +63,22 @@ def test_reference_arm_runs_on_rank_zero_only(bench, monkeypatch, capsys):
     args = argparse.Namespace(gpus=2, steps=1, warmup=1, impl="reference", config="hbox32", no_cpu_baseline=False, no_extra=False)
     bench.run_reference(args)
     assert capsys.readouterr().out == ""
+
+
+def test_roofline_extras_use_the_survey_flop_counts(bench):
+    from samrs_b200.config import geometry
+    g = geometry("vit_h")
+    fw, fg = bench.attention_flops_per_encode(g)
+    assert fw / 1e9 == pytest.approx(115.09, abs=0.05) and fg / 1e9 == pytest.approx(343.60, abs=0.05)
+    prof = {"attn_window": (1.6, 56), "attn_global": (1.4, 8), "gemm_tc": (11.0, 262)}
+    ex = bench.roofline_extras(g, prof, prof_steps=2, masks_per_s_per_gpu=3840.0, prompts=32, tokens_per_prompt=7, peak_tf=1456.2)
+    assert ex["attn_window"]["achieved"] == pytest.approx(115.09 * 2 / 1.6, rel=1e-3)             # GFLOP / ms = TFLOP/s
+    assert ex["attn_global"]["achieved"] == pytest.approx(343.60 * 2 / 1.4, rel=1e-3)
+    assert ex["attn_window"]["launches_per_step"] == 28 and ex["attn_global"]["ms_per_step"] == pytest.approx(0.7)
+    # 3 840 masks/s = 120 tiles/s x 5 757.7 GFLOP per tile (179.9 GFLOP per mask)
+    assert ex["whole_step"]["gflop_per_tile"] / 32 == pytest.approx(179.9, abs=0.05)
+    assert ex["whole_step"]["achieved"] == pytest.approx(3840 * 179.93 / 1e3, rel=1e-3)
+    assert ex["whole_step"]["frac"] == pytest.approx(ex["whole_step"]["achieved"] / 1456.2)
+    # unknown token count (5-point prompts carry 11 tokens) or another geometry: the whole-step reading is left out, nothing raises
+    assert "whole_step" not in bench.roofline_extras(g, prof, 2, 3840.0, 32, 11, 1456.2)
+    assert "whole_step" not in bench.roofline_extras(geometry("vit_t64"), {}, 2, 100.0, 8, 7, 1456.2)
