@@ -43,7 +43,9 @@ int samrs_set_features(void* engine, const float* features, void* stream);
 /* replaces PromptEncoder.forward + MaskDecoder.forward as called by SamPredictor.predict_torch
  * -- predictor.py:222-235, modeling/prompt_encoder.py:128-173, modeling/mask_decoder.py:71-174.
  * boxes (B,4) xyxy | points (B,NP,2) + labels (B,NP) int32 | mask_in (B,1,256,256), each may be NULL,
- * all in the 1024 input frame.  lowres_out (B,C,256,256), iou_out (B,C); C = 3 if multimask else 1. */
+ * all in the 1024 input frame.  lowres_out (B,C,256,256), iou_out (B,C); C = 3 if multimask else 1.
+ * Ordered on `stream` like every other call; internally part of the work runs on an engine-owned stream that forks from and
+ * joins back into `stream` through events (parallel branches of the replayed graph). */
 int samrs_decode(void* engine, const float* boxes, const float* points, const int* labels, int NP,
                  const float* mask_in, int B, int multimask, float* lowres_out, float* iou_out, void* stream);
 
